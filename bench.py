@@ -1,0 +1,363 @@
+"""bench.py — latents quantized per second on the CCVS vector-quantizer path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|train] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic latents:
+    c2 (default, BASELINE configs[1]): BAIR-256 encode+decode, 64 clips x 16 frames x 16x16 latents,
+        K=1024, D=256, FP32, per GPU:  forward(z) -> (z_q, loss, (perplexity, _, indices)) and
+        embed_code(indices) through the reference-facing VectorQuantizer API.
+    c1: configs[0] geometry (16 frames), c3: Kinetics 8x8 / K=16384 shard, c4: large-codebook stress
+        shard (K=16384, D=256, 2^21 latents per GPU), train: c2 shape forward+backward+EMA update.
+`value`  : whole-job latents/s with the inputs resident in HBM (CUDA events, max over ranks).
+`e2e`    : same metric through the same API with HOST buffers (pinned H2D of z, D2H of indices/loss
+           inside the timed region).
+`roofline`: the dominant kernel (tcgen05 screening GEMM), 2*N*K*D FLOPs per launch / its mean
+           launch duration measured live with CUDA events on the launching stream.
+`cpu_baseline` / `--impl reference`: the oracle port of the reference's CPU path (torch-CPU FP32, all
+           host threads), timed on a bounded sample of the same workload.
+Multi-GPU (torchrun, one rank per GPU): latents are sharded by frame, codebook replicated, no
+data-path collective (weak scaling: per-GPU work fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (leading dims (clips, frames), C=D, h, w, K, description)
+    "c1": ((1, 16), 256, 16, 16, 1024, "BAIR-256 quantizer forward, 16 frames x 16x16 latents, K=1024, D=256"),
+    "c2": ((64, 16), 256, 16, 16, 1024, "BAIR-256 encode+decode, 64 clips x 16 frames x 16x16 latents, K=1024, D=256"),
+    "c3": ((128, 16), 256, 8, 8, 16384, "Kinetics-600 64p shard, 128 clips x 16 frames x 8x8 latents, K=16384, D=256"),
+    "c4": ((2048, 16), 256, 8, 8, 16384, "large-codebook stress shard, 2^21 latents, K=16384, D=256"),
+    "train": ((64, 16), 256, 16, 16, 1024, "training-mode quantizer (fwd+bwd+EMA update), c2 shape"),
+}
+METRIC = "latents_quantized_per_sec"
+UNIT = "latents/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(workload: str, device, seed: int):
+    """Distribution T: E ~ N(0,1); z = E[randint] + 0.5 N(0,1) laid out [clips, frames, C, h, w]."""
+    (clips, frames), D, h, w, K, _ = WORKLOADS[workload]
+    g = torch.Generator(device=device).manual_seed(seed)
+    cb = torch.randn(K, D, generator=g, device=device)
+    n = clips * frames * h * w
+    z = torch.empty(clips, frames, D, h, w, device=device)
+    # build frame by frame blocks to bound temporary memory
+    zf = z.view(clips * frames, D, h * w)
+    blk = max(1, (1 << 22) // (h * w * D))
+    for s in range(0, clips * frames, blk):
+        e = min(clips * frames, s + blk)
+        m = (e - s) * h * w
+        pick = torch.randint(0, K, (m,), generator=g, device=device)
+        rows = cb[pick] + 0.5 * torch.randn(m, D, generator=g, device=device)
+        zf[s:e] = rows.view(e - s, h * w, D).transpose(1, 2)
+    return z, cb, n
+
+
+def run_reference(args):
+    """The reference's own CPU path (oracle port, torch-CPU FP32, all host threads) on a bounded
+    sample of the workload.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vq_oracle
+    (clips, frames), D, h, w, K, desc = WORKLOADS[args.workload]
+    # bounded sample: at most 16384 latents per step (the N x K fp32 one-hot / distance matrices of the
+    # full batch do not fit the reference's dense algorithm), same geometry and distribution
+    sample_frames = max(1, min(clips * frames, 16384 // (h * w)))
+    if K >= 16384:
+        sample_frames = max(1, min(sample_frames, 4096 // (h * w)))
+    z, cb = vq_oracle.synth((sample_frames, D, h, w), K, D, "T", seed=1234)
+    n = sample_frames * h * w
+    threads = torch.get_num_threads()
+
+    def step():
+        with torch.no_grad():
+            res = vq_oracle.forward(z, cb, 0.25)
+            vq_oracle.embed_code(res.indices.view(sample_frames, h, w), cb)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n / dt
+    sample = f"{n} latents ({sample_frames} frames x {h}x{w}) per step, dense N x K algorithm, distribution T"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "K": K, "D": D, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(workload: str, budget_s: float = 10.0):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vq_oracle
+    (clips, frames), D, h, w, K, _ = WORKLOADS[workload]
+    sample_frames = max(1, min(clips * frames, (16384 if K < 16384 else 4096) // (h * w)))
+    z, cb = vq_oracle.synth((sample_frames, D, h, w), K, D, "T", seed=1234)
+    n = sample_frames * h * w
+
+    def step():
+        with torch.no_grad():
+            res = vq_oracle.forward(z, cb, 0.25)
+            vq_oracle.embed_code(res.indices.view(sample_frames, h, w), cb)
+
+    step()
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 3 or (time.perf_counter() - t0 < budget_s and reps < 200):
+        step()
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{reps} passes over {n} latents ({sample_frames} frames x {h}x{w}), dense reference algorithm, "
+                      f"torch-CPU FP32, {dt * 1e3:.1f} ms/pass"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--search-mode", default="auto", choices=["auto", "tensor", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ccvs_b200 import VectorQuantizer, ops
+    from ccvs_b200.quantize import EMAVectorQuantizer
+
+    (clips, frames), D, h, w, K, desc = WORKLOADS[args.workload]
+    z, cb, n_lat = make_inputs(args.workload, dev, 1234 + rank)
+    train = args.workload == "train"
+    if train:
+        vq = EMAVectorQuantizer(K, D, 0.25, decay=0.99, search_mode=args.search_mode).to(dev).train()
+        g_out = torch.randn_like(z)
+        z.requires_grad_(True)
+    else:
+        vq = VectorQuantizer(K, D, 0.25, search_mode=args.search_mode).to(dev).eval()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb)
+        if train:
+            vq.ema_sum.copy_(cb)
+            vq.ema_count.fill_(1.0)
+
+    def step(zin):
+        if train:
+            zin.grad = None
+            z_q, loss, (perp, _, idx) = vq(zin)
+            torch.autograd.backward([z_q, loss], [g_out, torch.ones_like(loss)])
+            return idx, loss, perp, zin.grad
+        with torch.no_grad():
+            z_q, loss, (perp, _, idx) = vq(zin)
+            dec = vq.embed_code(idx.view(clips * frames, h, w))
+        return idx, loss, perp, dec
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(args.warmup):
+        step(z)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILER.reset(timing=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step(z)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ops.PROFILER.launches
+    prof = ops.PROFILER.summary()
+    ops.PROFILER.reset(timing=False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step_max = float(t)
+    value = n_lat * world / (ms_step_max * 1e-3)
+
+    # ---------------- end-to-end with host buffers ----------------
+    z_host = torch.empty(z.shape, dtype=z.dtype, pin_memory=True)
+    z_host.copy_(z.detach())
+    idx_host = torch.empty(n_lat, dtype=torch.int64, pin_memory=True)
+    sc_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+    z_stage = torch.empty(z.shape, dtype=z.dtype, device=dev)
+
+    def e2e_step():
+        z_stage.copy_(z_host, non_blocking=True)
+        zin = z_stage.detach().requires_grad_(True) if train else z_stage
+        idx, loss, perp, _ = step(zin)
+        idx_host.copy_(idx.view(-1), non_blocking=True)
+        sc_host.copy_(torch.stack([loss.detach(), perp]), non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1) / e2e_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t)
+    e2e = {"value": n_lat * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": z.numel() * 4, "d2h_bytes_per_step": n_lat * 8 + 8,
+           "note": "forward+embed_code through ccvs_b200.VectorQuantizer; z from pinned host memory, indices+loss+"
+                   "perplexity read back; decoded latents stay on the device (they feed the decoder there)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel ----------------
+    bf16_peak, bf16_sust, hbm_peak, peak_src = peaks()
+    breakdown = {k: {"calls": c, "ms_per_step": tms / args.steps} for k, (c, tms) in prof.items()}
+    roof = None
+    if "ccvsq_screen" in prof:
+        calls, tms = prof["ccvsq_screen"]
+        flops = 2.0 * n_lat * K * D
+        ach = flops / (tms / calls * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "screen_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        roof = {"kernel": "screen_kernel (tcgen05 BF16 distance GEMM + fused candidate selection)", "bound": "tensor",
+                "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                "frac_of_sustained": ach / bf16_sust, "peak_source": f"{peak_src} (burst; kernel timed alone per launch)",
+                "ms_per_launch": tms / calls, "algorithmic_flops_per_launch": flops, "traffic": traffic}
+    else:
+        name = max(prof, key=lambda k: prof[k][1])
+        roof = {"kernel": name, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
+                "traffic": None}
+    # secondary: decode gather bandwidth (bytes = N*(4D+8))
+    extra = {}
+    if "ccvsq_gather" in prof:
+        calls, tms = prof["ccvsq_gather"]
+        gbs = n_lat * (4 * D + 8) / (tms / calls * 1e-3) / 1e9
+        extra["decode_gather"] = {"achieved_GBs": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "ms_per_launch": tms / calls}
+    if "ccvsq_assign" in prof:
+        calls, tms = prof["ccvsq_assign"]
+        gbs = n_lat * (8 * D + 8) / (tms / calls * 1e-3) / 1e9
+        extra["assign"] = {"achieved_GBs": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "ms_per_launch": tms / calls}
+
+    cpu = None if args.no_cpu_baseline or world > 1 else cpu_baseline(args.workload)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "K": K, "D": D, "latents_per_gpu": n_lat,
+                   "layout": [clips, frames, D, h, w], "distribution": "T (E~N(0,1), z=E[randint]+0.5N(0,1))",
+                   "search_mode": args.search_mode, "screen_operands": "bf16 (fp32 accumulate), fp32 rescoring",
+                   "l2": f"inputs larger than L2 ({z.numel() * 4 / 2**20:.0f} MiB of latents per step)",
+                   "parallelism": f"frame-sharded x{world}, codebook replicated, no data-path collective"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "kernel_breakdown": breakdown, "hbm_kernels": extra,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,202 @@
+// search_exact.cu — exact FP32 nearest-code search (no tensor cores).
+//
+// Reference: quantize.py:45-50.  d[n,k] = fl(fl(||z_n||^2 + ||e_k||^2) - 2*<z_n, e_k>) and a
+// first-occurrence argmin, without ever materialising the N x K matrix.  This is the parity
+// anchor on the GPU (pure FP32 FMA arithmetic), the path for shapes the tensor-core screen does
+// not cover (e_dim = 1 state quantizer, D not a multiple of 64, ...) and the fallback for rows
+// the screen flags as "too many candidates inside the margin".
+//
+// Tiling: a CTA owns 64 latent rows whose full D-vector stays resident in shared memory
+// (zs[D][64]); the codebook streams through in 64-code x 16-dim slabs.  256 threads, each a
+// 4 rows x 4 codes register tile.
+#include <math.h>
+#include "common.cuh"
+
+namespace ccvsq {
+
+constexpr int XR = 64;    // rows per CTA
+constexpr int XC = 64;    // codes per slab
+constexpr int XK = 16;    // dims per slab
+constexpr int XT = 256;   // threads
+
+__global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restrict__ z, Lay L,
+                                                          const float* __restrict__ E,
+                                                          const float* __restrict__ e_sq, int K,
+                                                          const int64_t* __restrict__ row_list,
+                                                          const int32_t* __restrict__ row_count,
+                                                          int64_t max_rows, int64_t* __restrict__ idx) {
+  extern __shared__ float smem[];
+  const int Dp = ((L.D + XK - 1) / XK) * XK;      // D padded to the slab depth
+  float* zs = smem;                               // [Dp][XR]
+  float* es = zs + (size_t)Dp * XR;               // [XK][XC]
+  float* zz = es + XK * XC;                       // [XR]
+  float* red_d = zz + XR;                         // [XR][16]
+  int* red_k = reinterpret_cast<int*>(red_d + XR * 16);   // [XR][16]
+  __shared__ int64_t row_id[XR];
+
+  const int64_t total_rows = row_list ? min((int64_t)__ldg(row_count), max_rows) : L.N;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  for (int64_t r0 = (int64_t)blockIdx.x * XR; r0 < total_rows; r0 += (int64_t)gridDim.x * XR) {
+    const int nr = (int)min((int64_t)XR, total_rows - r0);
+    __syncthreads();   // previous iteration done with smem
+    if (tid < XR) row_id[tid] = (tid < nr) ? (row_list ? row_list[r0 + tid] : r0 + tid) : -1;
+    __syncthreads();
+
+    // ---- stage the 64 rows: zs[j][r]
+    if (L.S == 1) {
+      for (int i = tid; i < XR * Dp; i += XT) {
+        const int r = i / Dp, j = i - r * Dp;
+        float v = 0.f;
+        const int64_t n = row_id[r];
+        if (n >= 0 && j < L.D) v = __ldg(z + n * L.D + j);   // S==1: row n is contiguous (mult folds in)
+        zs[j * XR + r] = v;
+      }
+    } else {
+      const int r = tid & (XR - 1);
+      const int64_t n = row_id[r];
+      int64_t base = 0;
+      if (n >= 0) {
+        const int64_t p = n / L.mult;
+        const int m = (int)(n - p * L.mult);
+        base = pos_base(L, p) + (int64_t)m * L.D * L.S;
+      }
+      for (int j = tid / XR; j < Dp; j += XT / XR) {
+        float v = 0.f;
+        if (n >= 0 && j < L.D) v = __ldg(z + base + (int64_t)j * L.S);
+        zs[j * XR + r] = v;
+      }
+    }
+    __syncthreads();
+    if (tid < XR) {
+      float acc = 0.f;
+      for (int j = 0; j < L.D; ++j) acc = fmaf(zs[j * XR + tid], zs[j * XR + tid], acc);
+      zz[tid] = acc;
+    }
+    // (zz is consumed after the next __syncthreads inside the slab loop)
+
+    float best_d[4];
+    int best_k[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { best_d[i] = INFINITY; best_k[i] = 0x7fffffff; }
+
+    for (int k0 = 0; k0 < K; k0 += XC) {
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+
+      for (int j0 = 0; j0 < Dp; j0 += XK) {
+        __syncthreads();
+        // slab: es[jj][code] for 64 codes x 16 dims; thread -> (code = tid/4, 4 dims)
+        {
+          const int code = tid >> 2, jq = (tid & 3) * 4;
+          const int k = k0 + code;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + jq + u;
+            float v = 0.f;
+            if (k < K && j < L.D) v = __ldg(E + (size_t)k * L.D + j);
+            es[(jq + u) * XC + code] = v;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < XK; ++jj) {
+          const float4 zv = *reinterpret_cast<const float4*>(zs + (j0 + jj) * XR + ty * 4);
+          const float4 ev = *reinterpret_cast<const float4*>(es + jj * XC + tx * 4);
+          const float zr[4] = {zv.x, zv.y, zv.z, zv.w};
+          const float er[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(zr[i], er[c], acc[i][c]);
+        }
+      }
+      // distances for this slab of codes (increasing k within the thread -> strict '<' keeps first)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = k0 + tx * 4 + c;
+        if (k < K) {
+          const float ee = __ldg(e_sq + k);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float d = (zz[ty * 4 + i] + ee) - 2.f * acc[i][c];
+            if (d < best_d[i] || (d == best_d[i] && k < best_k[i])) { best_d[i] = d; best_k[i] = k; }
+          }
+        }
+      }
+    }
+    // ---- merge the 16 threads that share a row (lexicographic (d, k) minimum)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      red_d[(ty * 4 + i) * 16 + tx] = best_d[i];
+      red_k[(ty * 4 + i) * 16 + tx] = best_k[i];
+    }
+    __syncthreads();
+    if (tid < nr) {
+      float bd = red_d[tid * 16];
+      int bk = red_k[tid * 16];
+      for (int t = 1; t < 16; ++t) {
+        const float d = red_d[tid * 16 + t];
+        const int k = red_k[tid * 16 + t];
+        if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
+      }
+      idx[row_id[tid]] = (bk == 0x7fffffff) ? 0 : bk;
+    }
+  }
+}
+
+static size_t exact_smem_bytes(int D) {
+  const int Dp = ((D + XK - 1) / XK) * XK;
+  return ((size_t)Dp * XR + XK * XC + XR + XR * 16 * 2) * sizeof(float);
+}
+
+static int launch_exact(const float* z, const Lay& L, const float* E, const float* e_sq, int K,
+                        const int64_t* rows, const int32_t* row_count, int64_t max_rows, int64_t* idx,
+                        cudaStream_t st) {
+  const size_t smem = exact_smem_bytes(L.D);
+  CCVSQ_REQUIRE(smem <= 227 * 1024, CCVSQ_UNSUPPORTED,
+                "search_exact: D=%d needs %zu bytes of shared memory (> 227 KiB)", L.D, smem);
+  if (smem > 48 * 1024)
+    CCVSQ_CUDA(cudaFuncSetAttribute(search_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+  const int64_t work = rows ? max_rows : L.N;
+  int64_t blocks = (work + XR - 1) / XR;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  search_exact_kernel<<<(unsigned)blocks, XT, smem, st>>>(z, L, E, e_sq, K, rows, row_count, max_rows,
+                                                        idx);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+}  // namespace ccvsq
+
+using namespace ccvsq;
+
+extern "C" int ccvsq_search_exact(const float* z, ccvsq_layout lay, const float* E, const float* e_sq,
+                                  int K, int64_t* idx, void* stream) {
+  CCVSQ_REQUIRE(z && E && e_sq && idx, CCVSQ_NULL_POINTER, "search_exact: null pointer");
+  CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "search_exact: K=%d", K);
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  return launch_exact(z, L, E, e_sq, K, nullptr, nullptr, 0, idx, (cudaStream_t)stream);
+}
+
+extern "C" int ccvsq_search_exact_rows(const float* z, ccvsq_layout lay, const float* E,
+                                       const float* e_sq, int K, const int64_t* rows,
+                                       const int32_t* row_count, int64_t max_rows, int64_t* idx,
+                                       void* stream) {
+  CCVSQ_REQUIRE(z && E && e_sq && idx && rows && row_count, CCVSQ_NULL_POINTER,
+                "search_exact_rows: null pointer");
+  CCVSQ_REQUIRE(K > 0 && max_rows >= 0, CCVSQ_BAD_SHAPE, "search_exact_rows: K=%d max_rows=%lld", K,
+                (long long)max_rows);
+  if (max_rows == 0) return CCVSQ_OK;
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  return launch_exact(z, L, E, e_sq, K, rows, row_count, max_rows, idx, (cudaStream_t)stream);
+}

@@ -1,0 +1,651 @@
+// stream_kernels.cu — the HBM-bound kernels of the quantizer path (everything except the
+// tcgen05 screening GEMM): codebook preparation, latent packing, FP32 rescoring, assignment
+// (gather + straight-through value + squared error), decode gather, backward, per-code
+// scatter-reduce, finalize, EMA update.
+//
+// Common structure ("position tile"): a CTA stages PT=32 consecutive positions x C channels of
+// the latent tensor in shared memory.  For channel-major inputs (S>1, i.e. NCHW / NTCHW) the
+// global accesses are coalesced along the spatial index (lane = position), for row-contiguous
+// inputs (S==1) along the channel index.  The tile row stride is C+1 floats so that both the
+// position-major fill and the channel-major per-row sweeps are bank-conflict free.
+#include <math.h>
+#include "common.cuh"
+
+namespace ccvsq {
+
+constexpr int PT = 32;        // positions per tile
+constexpr int NT = 256;       // threads per CTA
+constexpr int NW = NT / 32;   // warps per CTA
+
+// ------------------------------------------------------------------------------------------------
+// tile movers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_load(const float* __restrict__ x, const Lay& L, int64_t p0,
+                                          int np, float* __restrict__ tile) {
+  const int CP = L.C + 1;
+  if (L.S == 1) {
+    const float* src = x + p0 * L.C;
+    const int total = np * L.C;
+    for (int i = threadIdx.x; i < total; i += NT) {
+      int p = i / L.C, c = i - p * L.C;
+      tile[p * CP + c] = __ldg(src + i);
+    }
+  } else {
+    const int p = threadIdx.x % PT;
+    if (p < np) {
+      const float* src = x + pos_base(L, p0 + p);
+      float* dst = tile + p * CP;
+      int c = threadIdx.x / PT;
+#pragma unroll 4
+      for (; c < L.C; c += NT / PT) dst[c] = __ldg(src + (int64_t)c * L.S);
+    }
+  }
+}
+
+// out[...] = tile (+ addend[...] if addend != nullptr)
+__device__ __forceinline__ void tile_store(float* __restrict__ out, const float* __restrict__ addend,
+                                           const Lay& L, int64_t p0, int np,
+                                           const float* __restrict__ tile) {
+  const int CP = L.C + 1;
+  if (L.S == 1) {
+    float* dst = out + p0 * L.C;
+    const float* add = addend ? addend + p0 * L.C : nullptr;
+    const int total = np * L.C;
+    for (int i = threadIdx.x; i < total; i += NT) {
+      int p = i / L.C, c = i - p * L.C;
+      float v = tile[p * CP + c];
+      if (add) v += __ldg(add + i);
+      dst[i] = v;
+    }
+  } else {
+    const int p = threadIdx.x % PT;
+    if (p < np) {
+      const int64_t base = pos_base(L, p0 + p);
+      const float* src = tile + p * CP;
+      int c = threadIdx.x / PT;
+#pragma unroll 4
+      for (; c < L.C; c += NT / PT) {
+        float v = src[c];
+        if (addend) v += __ldg(addend + base + (int64_t)c * L.S);
+        out[base + (int64_t)c * L.S] = v;
+      }
+    }
+  }
+}
+
+static inline size_t tile_smem_bytes(const Lay& L) { return (size_t)PT * (L.C + 1) * sizeof(float); }
+
+template <typename Kern>
+static int enable_smem(Kern kern, size_t bytes) {
+  CCVSQ_REQUIRE(bytes <= 227 * 1024, CCVSQ_UNSUPPORTED,
+                "tile needs %zu bytes of shared memory (> 227 KiB): C too large", bytes);
+  if (bytes > 48 * 1024)
+    CCVSQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return CCVSQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepare_codebook: one warp per (padded) code row
+// ------------------------------------------------------------------------------------------------
+__global__ void prepare_codebook_kernel(const float* __restrict__ E, int K, int K_pad, int D,
+                                        float* __restrict__ e_sq, __nv_bfloat16* __restrict__ Eb,
+                                        float* __restrict__ bias, unsigned int* __restrict__ e_max_bits) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= K_pad) return;
+  if (k >= K) {
+    if (Eb)
+      for (int j = lane; j < D; j += 32) Eb[(size_t)k * D + j] = __float2bfloat16_rn(0.f);
+    if (bias && lane == 0) bias[k] = -INFINITY;
+    return;
+  }
+  const float* e = E + (size_t)k * D;
+  float acc = 0.f;
+  for (int j = lane; j < D; j += 32) {
+    float v = e[j];
+    acc = fmaf(v, v, acc);
+    if (Eb) Eb[(size_t)k * D + j] = __float2bfloat16_rn(v);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    e_sq[k] = acc;
+    if (bias) bias[k] = -0.5f * acc;
+    if (e_max_bits) atomicMax(e_max_bits, __float_as_uint(sqrtf(acc)));  // acc >= 0: uint order == float order
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack_latents: any layout -> row-major bf16 [N_pad, D] + per-row margin
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) pack_latents_kernel(const float* __restrict__ z, Lay L,
+                                                          __nv_bfloat16* __restrict__ zb,
+                                                          float* __restrict__ row_margin,
+                                                          float margin_scale,
+                                                          const float* __restrict__ e_max,
+                                                          int64_t N_pad) {
+  extern __shared__ float tile[];
+  if (e_max) margin_scale *= __ldg(e_max);
+  const int CP = L.C + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_tile = PT * L.mult;
+  const int64_t n0 = p0 * L.mult;
+  if (p0 >= L.P) {
+    // pure padding tile: zero rows [n0, min(n0 + rows, N_pad))
+    for (int r = warp; r < rows_per_tile; r += NW) {
+      int64_t n = n0 + r;
+      if (n >= N_pad) break;
+      for (int j = lane; j < L.D; j += 32) zb[n * L.D + j] = __float2bfloat16_rn(0.f);
+      if (lane == 0) row_margin[n] = 0.f;
+    }
+    return;
+  }
+  const int np = (int)min((int64_t)PT, L.P - p0);
+  tile_load(z, L, p0, np, tile);
+  __syncthreads();
+  for (int r = warp; r < rows_per_tile; r += NW) {
+    const int64_t n = n0 + r;
+    if (n >= N_pad) break;
+    const int p = r / L.mult, m = r - p * L.mult;
+    if (p < np) {
+      const float* t = tile + p * CP + m * L.D;
+      float acc = 0.f;
+      for (int j = lane; j < L.D; j += 32) {
+        float v = t[j];
+        acc = fmaf(v, v, acc);
+        zb[n * L.D + j] = __float2bfloat16_rn(v);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) row_margin[n] = margin_scale * sqrtf(acc);
+    } else {
+      for (int j = lane; j < L.D; j += 32) zb[n * L.D + j] = __float2bfloat16_rn(0.f);
+      if (lane == 0) row_margin[n] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rescore: FP32 re-evaluation of screened candidates (reference formula, lowest-index ties)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) rescore_kernel(const float* __restrict__ z, Lay L,
+                                                     const float* __restrict__ E,
+                                                     const float* __restrict__ e_sq, int K,
+                                                     const int32_t* __restrict__ cand, int n_cand,
+                                                     const uint8_t* __restrict__ flags,
+                                                     int64_t* __restrict__ idx,
+                                                     int64_t* __restrict__ fb_rows,
+                                                     int32_t* __restrict__ fb_count, int64_t fb_cap) {
+  extern __shared__ float tile[];
+  __shared__ int need_tile;
+  const int CP = L.C + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int np = (int)min((int64_t)PT, L.P - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = np * L.mult;
+  const int64_t n0 = p0 * L.mult;
+
+  // Pass 0: rows with exactly one candidate are final; find out whether the tile needs z at all.
+  if (threadIdx.x == 0) need_tile = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < rows; r += NT) {
+    const int64_t n = n0 + r;
+    const int32_t c0 = cand[n * n_cand];
+    const bool multi = (n_cand > 1 && cand[n * n_cand + 1] >= 0) || c0 < 0;
+    if (multi) need_tile = 1;
+    else idx[n] = c0;
+    if (flags && (flags[n] & 1) && fb_rows) {
+      int slot = atomicAdd(fb_count, 1);
+      if (slot < fb_cap) fb_rows[slot] = n;
+    }
+  }
+  __syncthreads();
+  if (!need_tile) return;
+
+  tile_load(z, L, p0, np, tile);
+  __syncthreads();
+  for (int r = warp; r < rows; r += NW) {
+    const int64_t n = n0 + r;
+    const int32_t* cr = cand + n * n_cand;
+    if (!(n_cand > 1 && cr[1] >= 0) && cr[0] >= 0) continue;  // single candidate: done in pass 0
+    const int p = r / L.mult, m = r - p * L.mult;
+    const float* t = tile + p * CP + m * L.D;
+    float zz = 0.f;
+    for (int j = lane; j < L.D; j += 32) zz = fmaf(t[j], t[j], zz);
+    zz = warp_sum(zz);
+    float best_d = INFINITY;
+    int best_k = 0x7fffffff;
+    for (int c = 0; c < n_cand; ++c) {
+      const int k = cr[c];
+      if (k < 0 || k >= K) continue;
+      const float* e = E + (size_t)k * L.D;
+      float dot = 0.f;
+      for (int j = lane; j < L.D; j += 32) dot = fmaf(t[j], __ldg(e + j), dot);
+      dot = warp_sum(dot);
+      const float d = (zz + __ldg(e_sq + k)) - 2.f * dot;   // quantize.py:45-47 association
+      if (d < best_d || (d == best_d && k < best_k)) { best_d = d; best_k = k; }
+    }
+    if (lane == 0) idx[n] = (best_k == 0x7fffffff) ? 0 : best_k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// assign: zq = fl(z + fl(E[idx]-z)), sq_err += sum (E[idx]-z)^2, counts[idx]++
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) assign_kernel(const float* __restrict__ z, Lay L,
+                                                    const float* __restrict__ E, int K,
+                                                    const int64_t* __restrict__ idx,
+                                                    float* __restrict__ zq, double* __restrict__ sq_err,
+                                                    int32_t* __restrict__ counts) {
+  extern __shared__ float tile[];
+  __shared__ float red[NW];
+  const int CP = L.C + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int np = (int)min((int64_t)PT, L.P - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = np * L.mult;
+  const int64_t n0 = p0 * L.mult;
+  tile_load(z, L, p0, np, tile);
+  __syncthreads();
+  float acc = 0.f;
+  for (int r = warp; r < rows; r += NW) {
+    const int64_t n = n0 + r;
+    int64_t k = idx[n];
+    k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+    const int p = r / L.mult, m = r - p * L.mult;
+    float* t = tile + p * CP + m * L.D;
+    const float* e = E + (size_t)k * L.D;
+    for (int j = lane; j < L.D; j += 32) {
+      const float zv = t[j];
+      const float diff = __fsub_rn(__ldg(e + j), zv);   // fl(E[idx] - z)
+      t[j] = __fadd_rn(zv, diff);                       // fl(z + fl(E[idx] - z))   (quantize.py:64)
+      acc = fmaf(diff, diff, acc);
+    }
+    if (counts && lane == 0) atomicAdd(counts + k, 1);
+  }
+  if (sq_err) {
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+  }
+  __syncthreads();
+  if (sq_err && threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w];
+    atomicAdd(sq_err, (double)s);
+  }
+  if (zq) tile_store(zq, nullptr, L, p0, np, tile);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: dz = g_zq + (2 g_loss / M) (z - E[idx])
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) backward_dz_kernel(const float* __restrict__ z, Lay L,
+                                                         const float* __restrict__ E, int K,
+                                                         const int64_t* __restrict__ idx,
+                                                         const float* __restrict__ g_zq,
+                                                         const float* __restrict__ g_loss,
+                                                         float inv_M2, float* __restrict__ dz) {
+  extern __shared__ float tile[];
+  const int CP = L.C + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int np = (int)min((int64_t)PT, L.P - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = np * L.mult;
+  const int64_t n0 = p0 * L.mult;
+  const float coef = __ldg(g_loss) * inv_M2;
+  tile_load(z, L, p0, np, tile);
+  __syncthreads();
+  for (int r = warp; r < rows; r += NW) {
+    const int64_t n = n0 + r;
+    int64_t k = idx[n];
+    k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+    const int p = r / L.mult, m = r - p * L.mult;
+    float* t = tile + p * CP + m * L.D;
+    const float* e = E + (size_t)k * L.D;
+    for (int j = lane; j < L.D; j += 32) t[j] = coef * (t[j] - __ldg(e + j));
+  }
+  __syncthreads();
+  tile_store(dz, g_zq, L, p0, np, tile);
+}
+
+// ------------------------------------------------------------------------------------------------
+// code_stats: resid[k,:] += x_n - sub*E[k]; counts[k]++      (global fp32 reductions)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) code_stats_kernel(const float* __restrict__ x, Lay L,
+                                                        const float* __restrict__ E, int K,
+                                                        const int64_t* __restrict__ idx, float sub,
+                                                        float* __restrict__ resid,
+                                                        int32_t* __restrict__ counts) {
+  extern __shared__ float tile[];
+  const int CP = L.C + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int np = (int)min((int64_t)PT, L.P - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = np * L.mult;
+  const int64_t n0 = p0 * L.mult;
+  tile_load(x, L, p0, np, tile);
+  __syncthreads();
+  for (int r = warp; r < rows; r += NW) {
+    const int64_t n = n0 + r;
+    int64_t k = idx[n];
+    if (k < 0 || k >= K) continue;
+    const int p = r / L.mult, m = r - p * L.mult;
+    const float* t = tile + p * CP + m * L.D;
+    float* dst = resid + (size_t)k * L.D;
+    if (sub != 0.f) {
+      const float* e = E + (size_t)k * L.D;
+      for (int j = lane; j < L.D; j += 32) atomicAdd(dst + j, t[j] - sub * __ldg(e + j));
+    } else {
+      for (int j = lane; j < L.D; j += 32) atomicAdd(dst + j, t[j]);
+    }
+    if (counts && lane == 0) atomicAdd(counts + k, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode gather, row-major output: one warp per row, 128-bit loads/stores when D % 4 == 0
+// ------------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(NT) gather_rows_kernel(const int64_t* __restrict__ code,
+                                                         const float* __restrict__ E, int K, int D,
+                                                         int64_t N, float* __restrict__ out,
+                                                         int32_t* __restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * NW + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * NW;
+  constexpr int RPW = 4;  // rows in flight per warp
+  for (int64_t n_base = warp_global * RPW; n_base < N; n_base += nwarps * RPW) {
+    int64_t k[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int64_t n = n_base + i;
+      int64_t kk = (n < N) ? __ldg(code + n) : 0;
+      if (kk < 0 || kk >= K) {
+        if (err_flag && lane == 0 && n < N) atomicOr(err_flag, 1);
+        kk = 0;
+      }
+      k[i] = kk;
+    }
+    if (VEC4) {
+      const int D4 = D >> 2;
+      for (int j = lane; j < D4; j += 32) {
+        float4 v[RPW];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(E + (size_t)k[i] * D) + j);
+#pragma unroll
+        for (int i = 0; i < RPW; ++i)
+          if (n_base + i < N) __stcs(reinterpret_cast<float4*>(out + (size_t)(n_base + i) * D) + j, v[i]);
+      }
+    } else {
+      for (int j = lane; j < D; j += 32) {
+#pragma unroll
+        for (int i = 0; i < RPW; ++i)
+          if (n_base + i < N) out[(size_t)(n_base + i) * D + j] = __ldg(E + (size_t)k[i] * D + j);
+      }
+    }
+  }
+}
+
+// decode gather, channel-major output (fused NHWC->NCHW of quantized_video_model.py:833)
+__global__ void __launch_bounds__(NT) gather_cm_kernel(const int64_t* __restrict__ code,
+                                                       const float* __restrict__ E, int K, Lay L,
+                                                       float* __restrict__ out,
+                                                       int32_t* __restrict__ err_flag) {
+  extern __shared__ float tile[];
+  const int CP = L.C + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int np = (int)min((int64_t)PT, L.P - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = np * L.mult;
+  const int64_t n0 = p0 * L.mult;
+  for (int r = warp; r < rows; r += NW) {
+    int64_t k = __ldg(code + n0 + r);
+    if (k < 0 || k >= K) {
+      if (err_flag && lane == 0) atomicOr(err_flag, 1);
+      k = 0;
+    }
+    const int p = r / L.mult, m = r - p * L.mult;
+    float* t = tile + p * CP + m * L.D;
+    const float* e = E + (size_t)k * L.D;
+    for (int j = lane; j < L.D; j += 32) t[j] = __ldg(e + j);
+  }
+  __syncthreads();
+  tile_store(out, nullptr, L, p0, np, tile);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: dE, loss, perplexity
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ resid,
+                                                       const int32_t* __restrict__ counts,
+                                                       const double* __restrict__ sq_err,
+                                                       const float* __restrict__ g_loss, int K, int D,
+                                                       double M, double N, float beta,
+                                                       float* __restrict__ dE, float* __restrict__ loss,
+                                                       float* __restrict__ perplexity) {
+  if (dE && resid) {
+    const float coef = -(float)(2.0 * (double)beta / M) * __ldg(g_loss);
+    const size_t total = (size_t)K * D;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x)
+      dE[i] = coef * resid[i];
+  }
+  if (blockIdx.x != 0) return;
+  if (loss && sq_err && threadIdx.x == 0) {
+    // quantize.py:60-61: mean((zq-z)^2) + beta*mean((zq-z)^2)
+    const float mse = (float)(*sq_err / M);
+    *loss = mse + beta * mse;
+  }
+  if (perplexity && counts) {
+    __shared__ float red[8];
+    float acc = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float p = (float)((double)counts[k] / N);
+      acc += p * logf(p + 1e-10f);   // quantize.py:68
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += red[w];
+      *perplexity = expf(-s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// EMA codebook update (extension, see header)
+// ------------------------------------------------------------------------------------------------
+__global__ void ema_counts_kernel(float* __restrict__ n_ema, const int32_t* __restrict__ counts, int K,
+                                  float decay, float* __restrict__ n_total) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = decay * n_ema[k] + (1.f - decay) * (float)counts[k];
+    n_ema[k] = v;
+    acc += v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    *n_total = s;
+  }
+}
+
+__global__ void ema_embed_kernel(float* __restrict__ E, const float* __restrict__ n_ema,
+                                 float* __restrict__ sum_ema, const float* __restrict__ resid,
+                                 const int32_t* __restrict__ counts, int K, int D, float decay,
+                                 float eps, const float* __restrict__ n_total) {
+  const size_t total = (size_t)K * D;
+  const float nt = *n_total;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / D);
+    const float s_batch = resid[i] + (float)counts[k] * E[i];   // sum of latents assigned to k
+    const float s = decay * sum_ema[i] + (1.f - decay) * s_batch;
+    sum_ema[i] = s;
+    const float n_smooth = (n_ema[k] + eps) / (nt + (float)K * eps) * nt;   // Laplace smoothing
+    E[i] = s / n_smooth;
+  }
+}
+
+}  // namespace ccvsq
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace ccvsq;
+
+extern "C" int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf16,
+                                      float* bias, float* e_max, void* stream) {
+  CCVSQ_REQUIRE(E && e_sq, CCVSQ_NULL_POINTER, "prepare_codebook: E and e_sq must be non-null");
+  CCVSQ_REQUIRE(K > 0 && D > 0, CCVSQ_BAD_SHAPE, "prepare_codebook: K=%d D=%d", K, D);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K_pad = (E_bf16 || bias) ? ((K + 255) / 256) * 256 : K;
+  if (e_max) CCVSQ_CUDA(cudaMemsetAsync(e_max, 0, sizeof(float), st));
+  const int wpb = 8;
+  prepare_codebook_kernel<<<cdiv(K_pad, wpb), wpb * 32, 0, st>>>(
+      E, K, K_pad, D, e_sq, (__nv_bfloat16*)E_bf16, bias, (unsigned int*)e_max);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_pack_latents(const float* z, ccvsq_layout lay, void* z_bf16, float* row_margin,
+                                  float margin_scale, const float* e_max, void* stream) {
+  CCVSQ_REQUIRE(z && z_bf16 && row_margin, CCVSQ_NULL_POINTER, "pack_latents: null pointer");
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  const int64_t N_pad = ((L.N + 127) / 128) * 128;
+  const int64_t tiles = (N_pad + (int64_t)PT * L.mult - 1) / ((int64_t)PT * L.mult);
+  const size_t smem = tile_smem_bytes(L);
+  if (int rc = enable_smem(pack_latents_kernel, smem)) return rc;
+  pack_latents_kernel<<<(unsigned)tiles, NT, smem, (cudaStream_t)stream>>>(
+      z, L, (__nv_bfloat16*)z_bf16, row_margin, margin_scale, e_max, N_pad);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, const float* e_sq, int K,
+                             const int32_t* cand_idx, int n_cand, const uint8_t* flags, int64_t* idx,
+                             int64_t* fallback_rows, int32_t* fallback_count, int64_t fallback_capacity,
+                             void* stream) {
+  CCVSQ_REQUIRE(z && E && e_sq && cand_idx && idx, CCVSQ_NULL_POINTER, "rescore: null pointer");
+  CCVSQ_REQUIRE(n_cand >= 1 && n_cand <= CCVSQ_MAX_CAND, CCVSQ_BAD_SHAPE, "rescore: n_cand=%d", n_cand);
+  CCVSQ_REQUIRE((fallback_rows == nullptr) == (fallback_count == nullptr), CCVSQ_NULL_POINTER,
+                "rescore: fallback_rows and fallback_count must be given together");
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  const size_t smem = tile_smem_bytes(L);
+  if (int rc = enable_smem(rescore_kernel, smem)) return rc;
+  rescore_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(
+      z, L, E, e_sq, K, cand_idx, n_cand, flags, idx, fallback_rows, fallback_count, fallback_capacity);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_assign(const float* z, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
+                            float* zq_out, double* sq_err, int32_t* counts, void* stream) {
+  CCVSQ_REQUIRE(z && E && idx, CCVSQ_NULL_POINTER, "assign: null pointer");
+  CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "assign: K=%d", K);
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  const size_t smem = tile_smem_bytes(L);
+  if (int rc = enable_smem(assign_kernel, smem)) return rc;
+  assign_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(z, L, E, K, idx, zq_out,
+                                                                          sq_err, counts);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_backward_dz(const float* z, ccvsq_layout lay, const float* E, int K,
+                                 const int64_t* idx, const float* g_zq, const float* g_loss, float* dz,
+                                 void* stream) {
+  CCVSQ_REQUIRE(z && E && idx && g_loss && dz, CCVSQ_NULL_POINTER, "backward_dz: null pointer");
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  const size_t smem = tile_smem_bytes(L);
+  if (int rc = enable_smem(backward_dz_kernel, smem)) return rc;
+  const double M = (double)L.P * L.C;
+  backward_dz_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(
+      z, L, E, K, idx, g_zq, g_loss, (float)(2.0 / M), dz);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_code_stats(const float* x, ccvsq_layout lay, const float* E, int K,
+                                const int64_t* idx, float sub, float* resid, int32_t* counts,
+                                void* stream) {
+  CCVSQ_REQUIRE(x && idx && resid, CCVSQ_NULL_POINTER, "code_stats: null pointer");
+  CCVSQ_REQUIRE(sub == 0.f || E, CCVSQ_NULL_POINTER, "code_stats: E required when sub != 0");
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  const size_t smem = tile_smem_bytes(L);
+  if (int rc = enable_smem(code_stats_kernel, smem)) return rc;
+  code_stats_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(x, L, E, K, idx, sub,
+                                                                              resid, counts);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_gather(const int64_t* code, const float* E, int K, ccvsq_layout out_lay, float* out,
+                            int32_t* err_flag, void* stream) {
+  CCVSQ_REQUIRE(code && E && out, CCVSQ_NULL_POINTER, "gather: null pointer");
+  CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "gather: K=%d", K);
+  Lay L;
+  if (int rc = make_lay(out_lay, &L)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L.S == 1) {
+    const int64_t warps_needed = (L.N + 3) / 4;
+    int64_t blocks = (warps_needed + NW - 1) / NW;
+    const int64_t cap = (int64_t)kNumSMs * 8 * 4;   // grid-stride beyond a few waves
+    if (blocks > cap) blocks = cap;
+    const bool vec = (L.D % 4 == 0) && (((uintptr_t)E | (uintptr_t)out) % 16 == 0);
+    if (vec)
+      gather_rows_kernel<true><<<(unsigned)blocks, NT, 0, st>>>(code, E, K, L.D, L.N, out, err_flag);
+    else
+      gather_rows_kernel<false><<<(unsigned)blocks, NT, 0, st>>>(code, E, K, L.D, L.N, out, err_flag);
+  } else {
+    const size_t smem = tile_smem_bytes(L);
+    if (int rc = enable_smem(gather_cm_kernel, smem)) return rc;
+    gather_cm_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, st>>>(code, E, K, L, out, err_flag);
+  }
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_finalize(const float* resid, const int32_t* counts, const double* sq_err,
+                              const float* g_loss, int K, int D, double M, double N, float beta,
+                              float* dE, float* loss, float* perplexity, void* stream) {
+  CCVSQ_REQUIRE(K > 0 && D > 0 && M > 0 && N > 0, CCVSQ_BAD_SHAPE, "finalize: K=%d D=%d M=%g N=%g", K,
+                D, M, N);
+  CCVSQ_REQUIRE(!dE || (resid && g_loss), CCVSQ_NULL_POINTER, "finalize: dE needs resid and g_loss");
+  CCVSQ_REQUIRE(!loss || sq_err, CCVSQ_NULL_POINTER, "finalize: loss needs sq_err");
+  CCVSQ_REQUIRE(!perplexity || counts, CCVSQ_NULL_POINTER, "finalize: perplexity needs counts");
+  int blocks = dE ? cdiv((int64_t)K * D, 256 * 8) : 1;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (blocks < 1) blocks = 1;
+  finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(resid, counts, sq_err, g_loss, K, D, M, N,
+                                                         beta, dE, loss, perplexity);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_ema_update(float* E, float* n_ema, float* sum_ema, const float* resid,
+                                const int32_t* counts, int K, int D, float decay, float eps,
+                                float* scratch, void* stream) {
+  CCVSQ_REQUIRE(E && n_ema && sum_ema && resid && counts && scratch, CCVSQ_NULL_POINTER,
+                "ema_update: null pointer");
+  CCVSQ_REQUIRE(K > 0 && D > 0, CCVSQ_BAD_SHAPE, "ema_update: K=%d D=%d", K, D);
+  cudaStream_t st = (cudaStream_t)stream;
+  ema_counts_kernel<<<1, 256, 0, st>>>(n_ema, counts, K, decay, scratch);
+  CCVSQ_LAUNCH_CHECK();
+  int blocks = cdiv((int64_t)K * D, 256 * 4);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  ema_embed_kernel<<<blocks, 256, 0, st>>>(E, n_ema, sum_ema, resid, counts, K, D, decay, eps, scratch);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}

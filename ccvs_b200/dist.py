@@ -1,0 +1,66 @@
+"""Multi-GPU plumbing for the quantizer path: one process per GPU, latents sharded by frame,
+codebook replicated (the reference shards the batch the same way, tools/engine.py:86-89).
+
+Forward / encode / decode need NO collective: indices and z_q stay on the owning rank.  Training
+statistics (per-code residual sums, counts, squared error) are exchanged with ONE all-reduce over a
+packed FP32 buffer  [resid: K*D | counts: K | sq_err hi, lo], after which every rank finalises
+identical dE / loss / perplexity / EMA state.  The reference-faithful mode instead leaves
+`embedding.weight.grad` local and lets the parent's DDP average it (tools/engine.py:71-74).
+
+Device-agnostic on purpose (pure torch ops + torch.distributed) so the packing/reduction logic is
+covered by world_size-2 gloo tests on CPU; on the GPU box the backend is NCCL over NVLink.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def frame_shard(total_frames: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, near-equal [start, stop) block of frames for `rank` (first `rem` ranks get one more)."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(total_frames, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def pack_stats(resid: torch.Tensor, counts: torch.Tensor, sq_err: torch.Tensor) -> torch.Tensor:
+    """[K, D] fp32, [K] int32, [1] fp64 -> one fp32 buffer.  Counts are exact in fp32 below 2^24 per
+    code; the fp64 squared error travels as a (hi, lo) fp32 pair."""
+    K, D = resid.shape
+    buf = torch.empty(K * D + K + 2, dtype=torch.float32, device=resid.device)
+    buf[: K * D] = resid.reshape(-1)
+    buf[K * D: K * D + K] = counts.to(torch.float32)
+    hi = sq_err.to(torch.float32)
+    lo = (sq_err - hi.to(torch.float64)).to(torch.float32)
+    buf[K * D + K] = hi.reshape(())
+    buf[K * D + K + 1] = lo.reshape(())
+    return buf
+
+
+def unpack_stats(buf: torch.Tensor, K: int, D: int):
+    resid = buf[: K * D].view(K, D)
+    counts = buf[K * D: K * D + K].round().to(torch.int32)
+    sq = buf[K * D + K].to(torch.float64) + buf[K * D + K + 1].to(torch.float64)
+    return resid, counts, sq.reshape(1)
+
+
+def all_reduce_stats(resid: torch.Tensor, counts: torch.Tensor, sq_err: torch.Tensor,
+                     group: Optional[dist.ProcessGroup] = None):
+    """Sum the code statistics over all ranks with a single all-reduce; returns (resid, counts, sq_err).
+    A no-op when torch.distributed is not initialised or the world has one rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return resid, counts, sq_err
+    K, D = resid.shape
+    buf = pack_stats(resid, counts, sq_err)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return unpack_stats(buf, K, D)
+
+
+def world_info(group: Optional[dist.ProcessGroup] = None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1

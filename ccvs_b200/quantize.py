@@ -1,0 +1,300 @@
+"""Drop-in `VectorQuantizer` for CCVS, B200-native.
+
+Mirrors the reference module surface
+    /root/reference/models/skip_vid_generator/modules/quantize.py:7-83
+(same constructor, attributes, `forward` / `embed_code` signatures and return structure, the single
+parameter `embedding.weight`) so `QVidModel`, `StateModel` and `StftModel`
+(quantized_video_model.py:143, state_model.py:57, stft_model.py:59) can use it unmodified, while all
+arithmetic runs in libccvsq's sm_100a kernels through the C ABI of include/ccvsq.h.
+
+What differs by design:
+  * no N x K distance matrix, no one-hot GEMM: a BF16 tcgen05 screening GEMM with a fused running
+    candidate selection + FP32 re-scoring replaces quantize.py:45-55;
+  * `min_encodings` (quantize.py:51-52, never consumed by any caller) is materialised lazily;
+  * NCHW/NTCHW inputs are read and written in place: the two permute+contiguous copies of
+    quantize.py:40-41,71-72 are folded into the kernels' addressing;
+  * CUDA only.  A CPU tensor raises: there is no fallback path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import dist as vq_dist
+from . import ops
+from ._lib import Layout
+
+
+class LazyOneHot:
+    """Stand-in for the reference's dense `min_encodings` [N, K] (quantize.py:51-52).
+
+    No reference caller reads it; at the stress config it would be 128 GiB per GPU.
+    `.dense()` builds the real tensor on demand; `.shape`, `.dtype`, `.device` answer without
+    allocating.
+    """
+
+    def __init__(self, indices: torch.Tensor, n_e: int, dtype: torch.dtype):
+        self.indices = indices
+        self.n_e = n_e
+        self.dtype = dtype
+
+    @property
+    def shape(self):
+        return torch.Size((self.indices.shape[0], self.n_e))
+
+    @property
+    def device(self):
+        return self.indices.device
+
+    def dense(self) -> torch.Tensor:
+        out = torch.zeros(self.indices.shape[0], self.n_e, dtype=self.dtype, device=self.indices.device)
+        out.scatter_(1, self.indices.view(-1, 1), 1)
+        return out
+
+    def __repr__(self):
+        return f"LazyOneHot(shape={tuple(self.shape)}, device={self.device})"
+
+
+class _QuantizeFn(torch.autograd.Function):
+    """forward: search + assign + finalize; backward: dz kernel + per-code scatter-reduce.
+
+    Gradients (autograd of quantize.py:60-64):
+        dz = g_zq + (2 g_loss / M) (z - E[idx])
+        dE = (2 beta g_loss / M) (n_k E_k - sum_{i in k} z_i)
+    """
+
+    @staticmethod
+    def forward(ctx, z, weight, module):
+        lay = ops.layout_of(z.shape, module.e_dim, module.mult)
+        cb = module._prepared()
+        idx = ops.search(z, lay, cb, module.search_mode, module.n_cand, module.margin_tau, module.exact_fallback)
+        zq, sq, counts = ops.assign(z, lay, weight, idx)
+        K, D = weight.shape
+        M, N = float(z.numel()), float(lay.rows)
+        _, loss, perp = ops.finalize(K, D, M, N, module.beta, counts=counts, sq_err=sq, want_loss=True,
+                                     want_perplexity=True)
+        ctx.lay = lay
+        ctx.beta = module.beta
+        # the EMA variant rewrites the codebook in place right after forward: keep the version the
+        # indices were computed with for backward
+        ctx.save_for_backward(z, weight.detach().clone() if module._inplace_codebook_update else weight, idx)
+        ctx.mark_non_differentiable(idx, perp, counts)
+        return zq, loss, idx, perp, counts
+
+    @staticmethod
+    def backward(ctx, g_zq, g_loss, _gi, _gp, _gc):
+        z, weight, idx = ctx.saved_tensors
+        lay = ctx.lay
+        dev = z.device
+        if g_loss is None:
+            g_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        g_loss = g_loss.to(torch.float32).contiguous()
+        dz = dE = None
+        if ctx.needs_input_grad[0]:
+            g = None if g_zq is None else g_zq.to(torch.float32).contiguous()
+            dz = ops.backward_dz(z, lay, weight, idx, g, g_loss)
+        if ctx.needs_input_grad[1]:
+            K, D = weight.shape
+            resid, _ = ops.code_stats(z, lay, weight, K, idx, sub=1.0, want_counts=False)
+            dE, _, _ = ops.finalize(K, D, float(z.numel()), float(lay.rows), ctx.beta, resid=resid, g_loss=g_loss,
+                                    want_dE=True)
+        return dz, dE, None
+
+
+class _GatherFn(torch.autograd.Function):
+    """E[idx] written in z's layout, with the embedding backward as a per-code scatter-add.
+    Used by the `normalize=True` variant, whose remaining elementwise graph (quantize.py:56-64)
+    stays in autograd."""
+
+    @staticmethod
+    def forward(ctx, weight, idx, lay):
+        out, _ = ops.gather(idx, weight, lay if lay.S > 1 else None)
+        ctx.lay = lay
+        ctx.K = weight.shape[0]
+        ctx.save_for_backward(idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        resid, _ = ops.code_stats(g.contiguous(), ctx.lay, None, ctx.K, idx, sub=0.0, want_counts=False)
+        return resid, None, None
+
+
+class VectorQuantizer(nn.Module):
+    """Discretization bottleneck of the VQ-VAE — same contract as the reference (quantize.py:7-30).
+
+    Inputs:
+    - n_e : number of embeddings
+    - e_dim : dimension of embedding per position (divided by `mult` internally, quantize.py:21)
+    - beta : weight of the codebook term, quantize.py:60-61 (the reference hard-codes 0.25)
+    - mult : number of concatenated embeddings per position
+    - normalize : L2-normalise z_q over the channel dim (quantize.py:56-57)
+
+    B200-specific keyword-only knobs (defaults reproduce the reference's results):
+    - search_mode: 'auto' (tensor-core screen + FP32 rescoring when the shape allows, exact FP32
+      kernel otherwise), 'tensor', or 'exact'
+    - n_cand: candidate slots per latent kept by the screen (<= 8)
+    - margin_tau: screening margin in units of 2^-8 * ||z|| * max||e||
+    - exact_fallback: rows with more than n_cand codes inside the margin are re-searched exactly
+    """
+
+    def __init__(self, n_e, e_dim, beta, mult=1, normalize=False, *, search_mode: str = "auto", n_cand: int = 4,
+                 margin_tau: float = 1.0, exact_fallback: bool = True):
+        super().__init__()
+        self.n_e = n_e
+        assert e_dim % mult == 0
+        self.e_dim = e_dim // mult
+        self.beta = beta
+        self.mult = mult
+        self.normalize = normalize
+        self.search_mode = search_mode
+        self.n_cand = n_cand
+        self.margin_tau = margin_tau
+        self.exact_fallback = exact_fallback
+
+        self.embedding = nn.Embedding(self.n_e, self.e_dim)
+        if self.e_dim <= 1:
+            self.embedding.weight.data.uniform_(0, 1.0)          # quantize.py:27-28
+        else:
+            self.embedding.weight.data.uniform_(-1.0 / self.n_e, 1.0 / self.n_e)   # quantize.py:30
+        self._cb: Optional[ops.PreparedCodebook] = None
+        self._inplace_codebook_update = False
+        self.last_counts: Optional[torch.Tensor] = None   # int32 [K] usage of the last forward
+
+    # -- codebook side data (||e||^2, BF16 shadow, bias).  Rebuilt on EVERY call by default: the
+    # reference's Polyak averaging writes `param.data` in place (quantized_video_model.py:962-964),
+    # which does not bump the autograd version counter, so no cheap staleness test exists.  The
+    # rebuild is one pass over K*D floats (microseconds).  `freeze_codebook()` pins it for
+    # inference loops over a fixed codebook.
+    def _prepared(self) -> ops.PreparedCodebook:
+        cb = self._cb
+        w = self.embedding.weight
+        if cb is not None and cb.ptr == w.data_ptr() and cb.weight.device == w.device:
+            return cb
+        return ops.prepare_codebook(w)
+
+    def freeze_codebook(self):
+        """Cache the codebook side data until `unfreeze_codebook()` (caller promises not to
+        modify `embedding.weight` in between)."""
+        self._cb = ops.prepare_codebook(self.embedding.weight)
+        return self
+
+    def unfreeze_codebook(self):
+        self._cb = None
+        return self
+
+    def forward(self, z):
+        """z [b, (t,) c, (h, w)] -> (z_q, loss, (perplexity, min_encodings, min_encoding_indices))
+        exactly as quantize.py:32-74."""
+        if not z.is_cuda:
+            raise RuntimeError("ccvs_b200.VectorQuantizer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if z.dtype != torch.float32:
+            raise TypeError(f"the reference quantizer is FP32 end to end; got {z.dtype}")
+        z = z.contiguous()
+        w = self.embedding.weight
+        if self.normalize:
+            z_q, loss, idx, perp = self._forward_normalized(z, w)
+        else:
+            z_q, loss, idx, perp, counts = _QuantizeFn.apply(z, w, self)
+            self.last_counts = counts
+        idx2 = idx.view(-1, 1)
+        return z_q, loss, (perp, LazyOneHot(idx2, self.n_e, z.dtype), idx2)
+
+    def _forward_normalized(self, z, w):
+        # search + gather in our kernels; the normalisation and its chain rule stay in autograd
+        lay = ops.layout_of(z.shape, self.e_dim, self.mult)
+        cb = self._prepared()
+        with torch.no_grad():
+            idx = ops.search(z.detach(), lay, cb, self.search_mode, self.n_cand, self.margin_tau, self.exact_fallback)
+            counts = torch.bincount(idx, minlength=self.n_e).to(torch.int32)
+            _, _, perp = ops.finalize(self.n_e, self.e_dim, float(z.numel()), float(lay.rows), self.beta, counts=counts,
+                                      want_perplexity=True)
+        self.last_counts = counts
+        zq = _GatherFn.apply(w, idx, lay).view(z.shape)
+        ch_dim = -3 if z.ndim >= 4 else -1
+        zq = zq / torch.norm(zq, p=2, dim=ch_dim, keepdim=True)                     # quantize.py:56-57
+        loss = torch.mean((zq.detach() - z) ** 2) + self.beta * torch.mean((zq - z.detach()) ** 2)
+        zq = z + (zq - z).detach()
+        return zq, loss, idx, perp
+
+    @torch.no_grad()
+    def encode_indices(self, z):
+        """Indices only (what QVidModel.encode keeps, quantized_video_model.py:798-799): int64 [N]."""
+        if not z.is_cuda:
+            raise RuntimeError("CUDA only; there is no CPU fallback")
+        z = z.contiguous()
+        lay = ops.layout_of(z.shape, self.e_dim, self.mult)
+        return ops.search(z, lay, self._prepared(), self.search_mode, self.n_cand, self.margin_tau, self.exact_fallback)
+
+    def embed_code(self, code, channel_major_hw=None):
+        """E[code] (quantize.py:76-83).  `channel_major_hw=(h, w)` additionally fuses the caller's
+        NHWC->NCHW copy (quantized_video_model.py:833): code [G, h, w] -> [G, C, h, w]."""
+        w = self.embedding.weight
+        if not code.is_cuda:
+            raise RuntimeError("CUDA only; there is no CPU fallback")
+        code = code.contiguous()
+        if code.dtype != torch.int64:
+            code = code.to(torch.int64)
+        if channel_major_hw is not None:
+            h, wd = channel_major_hw
+            S = h * wd
+            n_pos = code.numel() // self.mult
+            lay = Layout(n_pos // S, self.e_dim * self.mult, S, self.mult)
+            out, err = ops.gather(code, w, lay)
+            z = out.view(-1, self.e_dim * self.mult, h, wd)
+        else:
+            z, err = ops.gather(code, w)
+            if self.mult > 1:
+                s = list(z.shape)
+                s[-1] *= self.mult
+                s[-2] //= self.mult
+                z = z.view(s)
+        self._last_gather_err = err   # device flag: nonzero if a code was outside [0, n_e)
+        return z
+
+    def check_codes(self):
+        """Synchronising check of the last embed_code (nn.Embedding raises on out-of-range codes)."""
+        err = getattr(self, "_last_gather_err", None)
+        if err is not None and int(err.item()) != 0:
+            raise IndexError("embed_code: index out of range in codebook")
+
+
+class EMAVectorQuantizer(VectorQuantizer):
+    """EXTENSION (not in the reference): codebook trained by exponential-moving-average statistics
+    instead of the reference's Adam-on-codebook-loss (`--q_use_ema` in the reference is a
+    Polyak average of all weights, not this).  Parity for this class is pinned only against the
+    textbook restatement in oracle/vq_oracle.py::ema_update ("parity unpinned" w.r.t. the reference).
+
+    Per training forward:  per-code counts n_k and sums S_k of the assigned latents (one fused
+    scatter-reduce kernel) -> ONE packed all-reduce across ranks (ccvs_b200.dist) -> fused EMA kernel
+        N_k <- g N_k + (1-g) n_k ;  m_k <- g m_k + (1-g) S_k ;  E_k <- m_k / smooth(N_k)
+    """
+
+    def __init__(self, n_e, e_dim, beta, mult=1, *, decay: float = 0.99, eps: float = 1e-5, sync: bool = True, **kw):
+        super().__init__(n_e, e_dim, beta, mult=mult, normalize=False, **kw)
+        self.decay = decay
+        self.eps = eps
+        self.sync = sync
+        self.embedding.weight.requires_grad_(False)
+        self._inplace_codebook_update = True
+        self.register_buffer("ema_count", torch.zeros(n_e))
+        self.register_buffer("ema_sum", self.embedding.weight.detach().clone())
+
+    def forward(self, z):
+        out = super().forward(z)
+        if self.training:
+            with torch.no_grad():
+                zc = z.detach().contiguous()
+                w = self.embedding.weight
+                lay = ops.layout_of(zc.shape, self.e_dim, self.mult)
+                idx = out[2][2].view(-1)
+                resid, counts = ops.code_stats(zc, lay, w, self.n_e, idx, sub=1.0)
+                if self.sync:
+                    sq = torch.zeros(1, dtype=torch.float64, device=zc.device)
+                    resid, counts, _ = vq_dist.all_reduce_stats(resid, counts, sq)
+                    resid = resid.contiguous()
+                ops.ema_update(w, self.ema_count, self.ema_sum, resid, counts, self.decay, self.eps)
+        return out

@@ -1,0 +1,54 @@
+"""The C-ABI library loads and exports every symbol include/ccvsq.h declares; argument validation
+happens before any CUDA call (so these run without a GPU)."""
+import ctypes
+import os
+import re
+
+from ccvs_b200 import _lib
+
+
+def _declared_symbols():
+    text = open(_lib.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ccvsq_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exists_in_tree():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    assert os.path.commonpath([_lib.LIB_PATH, os.path.dirname(os.path.dirname(_lib.__file__))]) != "/"
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in ccvsq.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_version():
+    assert _lib.load().ccvsq_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)
+    assert lib.ccvsq_prepare_codebook(null, 4, 4, null, null, null, null, null) == -5    # NULL_POINTER
+    assert b"non-null" in lib.ccvsq_last_error()
+    assert lib.ccvsq_prepare_codebook(one, 0, 4, one, null, null, null, null) == -1       # BAD_SHAPE
+    bad = _lib.Layout(4, 6, 4, 4)      # C not divisible by mult
+    assert lib.ccvsq_search_exact(one, bad, one, one, 8, one, null) == -1
+    ok = _lib.Layout(4, 100, 4, 1)     # D = 100: not a tensor-core shape
+    assert lib.ccvsq_screen(one, one, one, one, 128, 256, 100, 4, one, one, one, null) == -2   # UNSUPPORTED
+    assert lib.ccvsq_screen(one, one, one, one, 128, 256, 128, 9, one, one, one, null) == -1   # n_cand > 8
+    assert lib.ccvsq_screen(ctypes.c_void_p(8), one, one, one, 128, 256, 128, 4, one, one, one, null) == -3  # MISALIGNED
+    assert lib.ccvsq_finalize(null, null, null, null, 4, 4, 0.0, 1.0, 0.25, null, null, null, null) == -1
+    del ok
+
+
+def test_layout_struct_matches_header():
+    assert ctypes.sizeof(_lib.Layout) == 24     # int64 + 3 x int32 (+4 pad)
+    assert _lib.Layout.G.offset == 0 and _lib.Layout.C.offset == 8 and _lib.Layout.mult.offset == 16

@@ -1,0 +1,288 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden fixtures and the CPU oracle.
+
+Tolerances (BASELINE.json north_star): indices bit-exact except documented near-ties (oracle FP32
+distance gap < 1e-6 relative); gathered embeddings bit-exact; z_q bit-exact given equal indices;
+loss / perplexity within 1e-5 relative; dz rtol 1e-5 / atol 1e-7; dE rtol 1e-4 / atol 1e-7
+(gradient tolerances are ours — north_star does not state them)."""
+import pytest
+import torch
+
+import vq_oracle
+from ccvs_b200 import VectorQuantizer, ops
+from ccvs_b200.quantize import EMAVectorQuantizer
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _modes(g):
+    modes = ["exact"]
+    if ops.tensor_path_supported(g.n_e, g.e_dim):
+        modes.append("tensor")
+    return modes
+
+
+def _build(g, mode):
+    vq = VectorQuantizer(g.n_e, g.e_dim_total, g.beta, mult=g.mult, normalize=g.normalize, search_mode=mode).to(DEV)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(g.codebook.to(DEV))
+    return vq
+
+
+def _check_indices(idx_ours, g):
+    ours = idx_ours.view(-1).cpu()
+    ref = g.indices.view(-1)
+    diff = ours != ref
+    if bool(diff.any()):
+        rows = vq_oracle.to_channel_last(g.z).reshape(-1, g.e_dim)
+        par = vq_oracle.classify_indices(ours, rows, g.codebook)
+        assert par.mismatch == 0, f"{par.mismatch} rows differ outside documented near-ties ({par})"
+    return not bool(diff.any())
+
+
+def test_golden_forward_backward(golden):
+    g = golden
+    for mode in _modes(g):
+        vq = _build(g, mode)
+        z = g.z.to(DEV).requires_grad_(True)
+        z_q, loss, (perp, one_hot, idx) = vq(z)
+        assert z_q.shape == z.shape and idx.shape == (g.indices.shape[0], 1) and idx.dtype == torch.int64
+        assert tuple(one_hot.shape) == (g.indices.shape[0], g.n_e)
+        ((z_q * g.g_zq.to(DEV)).sum() + loss * g.g_loss).backward()
+        same = _check_indices(idx, g)
+        if same:
+            if g.normalize:
+                torch.testing.assert_close(z_q.detach().cpu(), g.z_q, rtol=1e-6, atol=1e-7)
+            else:
+                assert torch.equal(z_q.detach().cpu(), g.z_q), f"{g.name}/{mode}: z_q not bitwise fl(z+fl(e-z))"
+            torch.testing.assert_close(loss.detach().cpu(), g.loss, rtol=1e-5, atol=0)
+            torch.testing.assert_close(perp.cpu(), g.perplexity, rtol=1e-5, atol=0)
+            assert torch.equal(one_hot.dense().sum(0).cpu(), g.one_hot_sum)
+            torch.testing.assert_close(z.grad.cpu(), g.dz, rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(vq.embedding.weight.grad.cpu(), g.dE, rtol=1e-4, atol=1e-7)
+        else:  # only near-ties differ (fresh-init fixture): loss still within tolerance
+            torch.testing.assert_close(loss.detach().cpu(), g.loss, rtol=1e-5, atol=0)
+
+
+def test_golden_embed_code(golden):
+    g = golden
+    if g.code is None:
+        return
+    vq = _build(g, "exact")
+    out = vq.embed_code(g.code.to(DEV))
+    vq.check_codes()
+    assert out.shape == g.embedded.shape
+    assert torch.equal(out.cpu(), g.embedded)        # pure gather: bit-exact
+
+
+def test_no_grad_and_eval_paths(golden):
+    g = golden
+    vq = _build(g, "auto").eval()
+    with torch.no_grad():
+        z_q, loss, (perp, _, idx) = vq(g.z.to(DEV))
+    assert not z_q.requires_grad and not loss.requires_grad
+    _check_indices(idx, g)
+    idx2 = vq.encode_indices(g.z.to(DEV))
+    assert torch.equal(idx2, idx.view(-1))
+
+
+# ------------------------------------------------------------------------------------------------
+# C-ABI level checks on seeded inputs (oracle finishes in well under a second at these sizes)
+# ------------------------------------------------------------------------------------------------
+CASES = [
+    # shape,                K,    D,   dist
+    ((16, 256, 16, 16), 1024, 256, "T"),     # BASELINE config 1
+    ((16, 256, 16, 16), 1024, 256, "I"),     # fresh-init stress: near-ties everywhere
+    ((4, 16, 512, 8, 8), 1024, 512, "T"),    # reference BAIR script shape
+    ((3, 64, 5, 7), 200, 64, "T"),           # ragged N and K
+    ((2, 128, 8, 8), 16384, 128, "T"),       # large codebook, few rows
+]
+
+
+@pytest.mark.parametrize("shape,K,D,dist", CASES)
+@pytest.mark.parametrize("mode", ["exact", "tensor"])
+def test_search_vs_oracle(shape, K, D, dist, mode):
+    z, cb = vq_oracle.synth(shape, K, D, dist, seed=1234)
+    lay = ops.layout_of(shape, D, 1)
+    pcb = ops.prepare_codebook(cb.to(DEV))
+    idx = ops.search(z.to(DEV), lay, pcb, mode=mode)
+    rows = vq_oracle.to_channel_last(z).reshape(-1, D)
+    par = vq_oracle.classify_indices(idx, rows, cb)
+    assert par.mismatch == 0, par
+    if dist == "T":
+        assert par.agreement >= 0.9999, par
+    torch.testing.assert_close(pcb.e_sq.cpu(), (cb ** 2).sum(1), rtol=1e-6, atol=0)
+
+
+def test_screen_scores_and_candidates():
+    """The tcgen05 GEMM itself: candidate scores equal <bf16(z), bf16(e)> - 0.5|e|^2 (FP32 accumulate)
+    and every code inside the margin is reported."""
+    shape, K, D = (8, 256, 8, 8), 1024, 256
+    z, cb = vq_oracle.synth(shape, K, D, "T", seed=7)
+    z = torch.randn_like(z)        # unit-variance latents against an N(0,1) codebook: real competition
+    lay = ops.layout_of(shape, D, 1)
+    pcb = ops.prepare_codebook(cb.to(DEV))
+    zb, margin = ops.pack_latents(z.to(DEV), lay, pcb, margin_tau=4.0)
+    sr = ops.screen(zb, margin, pcb, lay.rows, n_cand=8)
+    N = lay.rows
+    rows = vq_oracle.to_channel_last(z).reshape(-1, D).to(DEV)
+    assert torch.equal(zb[:N].float(), rows.to(torch.bfloat16).float())
+    torch.testing.assert_close(margin[:N], 4.0 * 2.0 ** -8 * rows.norm(dim=1) * cb.norm(dim=1).max().to(DEV), rtol=1e-5, atol=0)
+    s = zb[:N].float() @ pcb.e_bf16[:K].float().t() + pcb.bias[:K]
+    top = s.max(dim=1)
+    # FP32 accumulation order differs between the tensor core and torch.matmul: |s| ~ 1e2 -> 2e-2
+    torch.testing.assert_close(sr.cand_score[:, 0], top.values, rtol=1e-4, atol=2e-2)
+    # candidate 0 is an argmax up to accumulation-order noise
+    picked = s.gather(1, sr.cand_idx[:, :1].long()).squeeze(1)
+    assert bool((top.values - picked <= 2e-2).all())
+    # completeness: codes clearly inside the margin must be listed (unless the row overflowed)
+    inside = s >= (top.values - margin[:N] + 5e-2).unsqueeze(1)
+    n_inside = inside.sum(1)
+    ok_rows = (sr.flags == 0)
+    assert bool((n_inside[ok_rows] <= 8).all())
+    assert float(ok_rows.float().mean()) > 0.5
+    valid = sr.cand_idx >= 0
+    listed = torch.zeros(N, K + 1, dtype=torch.bool, device=DEV)
+    listed.scatter_(1, torch.where(valid, sr.cand_idx, torch.full_like(sr.cand_idx, K)).long(), True)
+    listed = listed[:, :K]
+    assert bool((listed[ok_rows] | ~inside[ok_rows]).all())
+    assert float((valid.sum(1) > 1).float().mean()) > 0.05      # the margin really admits rivals here
+    # candidates are sorted by score descending and unique
+    sc = sr.cand_score
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all())
+
+
+def test_overflow_rows_fall_back_to_exact():
+    """More identical codes than candidate slots: the screen flags the row, the exact kernel resolves
+    it to the lowest index (first-occurrence argmin, quantize.py:50)."""
+    K, D = 512, 64
+    torch.manual_seed(3)
+    cb = torch.randn(K, D)
+    cb[100:140] = cb[100]                         # 40 identical rows
+    z = cb[torch.tensor([100, 7, 120, 139])].repeat(64, 1) + 0.0
+    z = z.view(256, D)
+    lay = ops.rows_layout(256, D)
+    pcb = ops.prepare_codebook(cb.to(DEV))
+    idx = ops.search(z.to(DEV), lay, pcb, mode="tensor", n_cand=4).cpu()
+    expect = torch.tensor([100, 7, 100, 100]).repeat(64)
+    assert torch.equal(idx, expect)
+    zb, margin = ops.pack_latents(z.to(DEV), lay, pcb, 1.0)
+    sr = ops.screen(zb, margin, pcb, 256, 4)
+    assert bool((sr.flags.cpu().view(64, 4)[:, [0, 2, 3]] == 1).all())
+
+
+def test_assign_gather_backward_stats_finalize():
+    shape, K, D = (6, 128, 5, 9), 300, 128
+    z, cb = vq_oracle.synth(shape, K, D, "T", seed=11)
+    zc, cbc = z.to(DEV), cb.to(DEV)
+    lay = ops.layout_of(shape, D, 1)
+    rows = vq_oracle.to_channel_last(z).reshape(-1, D)
+    idx = vq_oracle.nearest(rows, cb)
+    idc = idx.to(DEV)
+    N, M = rows.shape[0], z.numel()
+
+    zq, sq, counts = ops.assign(zc, lay, cbc, idc)
+    e = cb[idx]
+    zq_ref = vq_oracle.to_channel_first((rows + (e - rows)).view(vq_oracle.to_channel_last(z).shape))
+    assert torch.equal(zq.cpu(), zq_ref)
+    sq_ref = float(((e - rows).double() ** 2).sum())
+    assert abs(float(sq) - sq_ref) <= 1e-5 * sq_ref
+    assert torch.equal(counts.cpu(), torch.bincount(idx, minlength=K).to(torch.int32))
+
+    out, err = ops.gather(idc, cbc)
+    assert int(err) == 0 and torch.equal(out.cpu(), e)
+    out_cm, _ = ops.gather(idc, cbc, lay)
+    assert torch.equal(out_cm.view(shape).cpu(), vq_oracle.to_channel_first(e.view(vq_oracle.to_channel_last(z).shape)))
+    bad = idc.clone()
+    bad[5] = K
+    _, err = ops.gather(bad, cbc)
+    assert int(err) == 1                       # nn.Embedding would raise; we flag, never read out of bounds
+
+    torch.manual_seed(5)
+    g_zq = torch.randn(shape)
+    g_loss = torch.tensor(0.37)
+    dz = ops.backward_dz(zc, lay, cbc, idc, g_zq.to(DEV), g_loss.to(DEV))
+    dz_rows = 2 * 0.37 * (rows - e) / M
+    dz_ref = vq_oracle.to_channel_first(dz_rows.view(vq_oracle.to_channel_last(z).shape)) + g_zq
+    torch.testing.assert_close(dz.cpu(), dz_ref, rtol=1e-5, atol=1e-7)
+    dz0 = ops.backward_dz(zc, lay, cbc, idc, None, g_loss.to(DEV))
+    torch.testing.assert_close(dz0.cpu(), dz_ref - g_zq, rtol=1e-5, atol=1e-7)
+
+    resid, cnt = ops.code_stats(zc, lay, cbc, K, idc, sub=1.0)
+    resid_ref = torch.zeros(K, D, dtype=torch.float64).index_add_(0, idx, (rows - e).double()).float()
+    torch.testing.assert_close(resid.cpu(), resid_ref, rtol=1e-4, atol=1e-5)
+    assert torch.equal(cnt.cpu(), counts.cpu())
+    sums, _ = ops.code_stats(zc, lay, None, K, idc, sub=0.0, want_counts=False)
+    sums_ref = torch.zeros(K, D, dtype=torch.float64).index_add_(0, idx, rows.double()).float()
+    torch.testing.assert_close(sums.cpu(), sums_ref, rtol=1e-4, atol=1e-5)
+
+    dE, loss, perp = ops.finalize(K, D, M, N, 0.25, resid=resid, counts=counts, sq_err=sq, g_loss=g_loss.to(DEV),
+                                  want_dE=True, want_loss=True, want_perplexity=True)
+    torch.testing.assert_close(dE.cpu(), -(2 * 0.25 * 0.37 / M) * resid_ref, rtol=1e-4, atol=1e-8)
+    res = vq_oracle.forward(z, cb, 0.25)
+    torch.testing.assert_close(loss.cpu(), res.loss, rtol=1e-5, atol=0)
+    torch.testing.assert_close(perp.cpu(), res.perplexity, rtol=1e-5, atol=0)
+
+
+def test_mult_and_flat_layouts_through_abi():
+    # mult > 1 on a channel-major tensor, and the ndim < 4 contiguous-row case incl. e_dim = 1
+    for shape, K, D, mult in [((3, 32, 4, 5), 64, 8, 4), ((50, 24), 16, 24, 1), ((4, 16, 2), 128, 1, 1)]:
+        z, cb = vq_oracle.synth(shape, K, D, "T" if D > 1 else "I", seed=21)
+        if D == 1:
+            cb = torch.rand(K, 1)
+        lay = ops.layout_of(shape, D, mult)
+        pcb = ops.prepare_codebook(cb.to(DEV))
+        idx = ops.search(z.to(DEV), lay, pcb, mode="exact")
+        res = vq_oracle.forward(z, cb, 0.25, mult)
+        par = vq_oracle.classify_indices(idx, vq_oracle.to_channel_last(z).reshape(-1, D), cb)
+        assert par.mismatch == 0, (shape, par)
+        if par.exact == par.n:
+            zq, sq, _ = ops.assign(z.to(DEV), lay, cb.to(DEV), idx)
+            assert torch.equal(zq.cpu(), res.z_q.detach())
+
+
+def test_single_code_and_tiny_inputs():
+    cb = torch.randn(1, 8)
+    z = torch.randn(1, 8, 1, 1)
+    lay = ops.layout_of(z.shape, 8, 1)
+    idx = ops.search(z.to(DEV), lay, ops.prepare_codebook(cb.to(DEV)), mode="auto")
+    assert idx.tolist() == [0]
+
+
+def test_ema_update_matches_textbook():
+    K, D = 64, 32
+    z, cb = vq_oracle.synth((4, 32, 6, 6), K, D, "T", seed=31)
+    rows = vq_oracle.to_channel_last(z).reshape(-1, D)
+    m = EMAVectorQuantizer(K, D, 0.25, decay=0.9, eps=1e-5, sync=False).to(DEV).train()
+    with torch.no_grad():
+        m.embedding.weight.copy_(cb.to(DEV))
+        m.ema_sum.copy_(cb.to(DEV))
+        m.ema_count.fill_(1.0)
+    idx_ref = vq_oracle.nearest(rows, cb)
+    new_cb, n, s = vq_oracle.ema_update(cb, torch.ones(K), cb.clone(), rows, idx_ref, 0.9, 1e-5)
+    zc = z.to(DEV).requires_grad_(True)
+    z_q, loss, (_, _, idx) = m(zc)
+    assert torch.equal(idx.view(-1).cpu(), idx_ref)
+    torch.testing.assert_close(m.ema_count.cpu(), n, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(m.ema_sum.cpu(), s, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(m.embedding.weight.cpu(), new_cb, rtol=1e-4, atol=1e-5)
+    loss.backward()       # backward uses the pre-update codebook
+    e = cb[idx_ref]
+    dz_ref = vq_oracle.to_channel_first((2 * (rows - e) / z.numel()).view(vq_oracle.to_channel_last(z).shape))
+    torch.testing.assert_close(zc.grad.cpu(), dz_ref, rtol=1e-5, atol=1e-7)
+
+
+def test_frozen_codebook_cache_and_polyak_update():
+    """Polyak averaging writes param.data in place (quantized_video_model.py:962-964): the default
+    (unfrozen) module must see the new codebook."""
+    z, cb = vq_oracle.synth((2, 64, 8, 8), 256, 64, "T", seed=41)
+    vq = VectorQuantizer(256, 64, 0.25).to(DEV)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+        i0 = vq(z.to(DEV))[2][2].clone()
+        perm = torch.randperm(256)
+        vq.embedding.weight.data.copy_(cb[perm].to(DEV))        # .data write: no version bump
+        i1 = vq(z.to(DEV))[2][2]
+    inv = torch.empty(256, dtype=torch.int64)
+    inv[perm] = torch.arange(256)
+    assert torch.equal(i1.view(-1).cpu(), inv[i0.view(-1).cpu()])   # permuting rows permutes indices
