@@ -246,25 +246,48 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
-    for _ in range(args.warmup):
-        step(z)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.PROFILER.reset(timing=True)
+    for _ in range(args.warmup):
+        step(z)
+    barrier()
+    # timed region: CUDA events on the launching stream; the dominant kernel (screen) is additionally
+    # bracketed by its own events so its launch duration is measured live inside the same region
+    ops.PROFILER.reset(timing={"ccvsq_screen", "ccvsq_search_exact"})
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         out = step(z)
     ev1.record()
+    host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = ops.PROFILER.launches
+    prof_main = ops.PROFILER.summary()
+    # keep the GPU under the same load until nvidia-smi has produced a few samples (its period is 100 ms,
+    # a short timed region can end before the first one)
+    t_extra0 = time.perf_counter()
+    extra_steps = 0
+    ops.PROFILER.reset(timing=False)
+    while rank == 0 and ms_total < 600.0 and time.perf_counter() - t_extra0 < 0.8:
+        step(z)
+        extra_steps += 1
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["note"] = f"sampled from warm-up through the timed region plus {extra_steps} identical untimed steps"
+    # per-kernel breakdown: separate pass with every entry point bracketed by events
+    ops.PROFILER.reset(timing=True)
+    for _ in range(args.steps):
+        step(z)
+    torch.cuda.synchronize()
     prof = ops.PROFILER.summary()
     ops.PROFILER.reset(timing=False)
-    clocks = sampler.stop() if rank == 0 else None
+    for k, v in prof_main.items():
+        prof[k] = v            # the dominant kernel's figure comes from the timed region itself
     ms_step = ms_total / args.steps
     t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
     if world > 1:
@@ -351,7 +374,7 @@ def main():
                    "search_mode": args.search_mode, "screen_operands": "bf16 (fp32 accumulate), fp32 rescoring",
                    "l2": f"inputs larger than L2 ({z.numel() * 4 / 2**20:.0f} MiB of latents per step)",
                    "parallelism": f"frame-sharded x{world}, codebook replicated, no data-path collective"},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "e2e": e2e, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "kernel_breakdown": breakdown, "hbm_kernels": extra,
     }
     print(json.dumps(line))

@@ -469,7 +469,7 @@ static int launch_screen(const CUtensorMap& ma, const CUtensorMap& mb, const flo
   const size_t smem = lay.total;
   CCVSQ_REQUIRE(smem <= 227 * 1024, CCVSQ_UNSUPPORTED, "screen: %zu bytes of shared memory needed", smem);
   auto kern = screen_kernel<BN, NST>;
-  CCVSQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (int rc = enable_smem(kern, smem)) return rc;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   kern<<<grid, SCREEN_THREADS, smem, st>>>(ma, mb, bias, row_margin, N, tiles, K, K_pad, dblk, n_cand,
                                          cand_idx, cand_score, flags, dbg_scores);

@@ -160,9 +160,7 @@ static int launch_exact(const float* z, const Lay& L, const float* E, const floa
   const size_t smem = exact_smem_bytes(L.D);
   CCVSQ_REQUIRE(smem <= 227 * 1024, CCVSQ_UNSUPPORTED,
                 "search_exact: D=%d needs %zu bytes of shared memory (> 227 KiB)", L.D, smem);
-  if (smem > 48 * 1024)
-    CCVSQ_CUDA(cudaFuncSetAttribute(search_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
+  if (int rc = enable_smem(search_exact_kernel, smem)) return rc;
   const int64_t work = rows ? max_rows : L.N;
   int64_t blocks = (work + XR - 1) / XR;
   const int64_t cap = (int64_t)kNumSMs * 16;

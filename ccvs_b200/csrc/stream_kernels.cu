@@ -75,15 +75,6 @@ __device__ __forceinline__ void tile_store(float* __restrict__ out, const float*
 
 static inline size_t tile_smem_bytes(const Lay& L) { return (size_t)PT * (L.C + 1) * sizeof(float); }
 
-template <typename Kern>
-static int enable_smem(Kern kern, size_t bytes) {
-  CCVSQ_REQUIRE(bytes <= 227 * 1024, CCVSQ_UNSUPPORTED,
-                "tile needs %zu bytes of shared memory (> 227 KiB): C too large", bytes);
-  if (bytes > 48 * 1024)
-    CCVSQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return CCVSQ_OK;
-}
-
 // ------------------------------------------------------------------------------------------------
 // prepare_codebook: one warp per (padded) code row
 // ------------------------------------------------------------------------------------------------

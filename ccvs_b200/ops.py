@@ -35,7 +35,8 @@ class Profiler:
         self.timing = False
         self.records = []      # (entry point, start event, end event)
 
-    def reset(self, timing: bool = False):
+    def reset(self, timing=False):
+        """timing: False | True (every entry point) | a set of entry-point names."""
         self.launches = 0
         self.timing = timing
         self.records = []
@@ -54,7 +55,7 @@ PROFILER = Profiler()
 
 def _call(name: str, *args) -> None:
     fn = getattr(_L, name)
-    if PROFILER.timing:
+    if PROFILER.timing is True or (PROFILER.timing and name in PROFILER.timing):
         s = torch.cuda.Event(enable_timing=True)
         e = torch.cuda.Event(enable_timing=True)
         s.record()
