@@ -81,22 +81,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Opt a kernel in to > 48 KiB of dynamic shared memory.  The attribute is per device and sticky, so
-// it is raised (never lowered) once per (kernel, device) instead of on every launch.
+// Opt a kernel in to > 48 KiB of dynamic shared memory.  The attribute is per (kernel, device) and
+// sticky, so it is raised once instead of on every launch (the table lives in api.cu).
+int enable_smem_impl(const void* kern, size_t bytes);
 template <typename Kern>
 inline int enable_smem(Kern kern, size_t bytes) {
-  CCVSQ_REQUIRE(bytes <= 227 * 1024, CCVSQ_UNSUPPORTED,
-                "tile needs %zu bytes of shared memory (> 227 KiB): C too large", bytes);
-  if (bytes > 48 * 1024) {
-    static thread_local size_t granted[16] = {0};
-    int dev = 0;
-    CCVSQ_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16 || granted[dev] < bytes) {
-      CCVSQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      if (dev >= 0 && dev < 16) granted[dev] = 227 * 1024;
-    }
-  }
-  return CCVSQ_OK;
+  return enable_smem_impl(reinterpret_cast<const void*>(kern), bytes);
 }
 
 constexpr int kNumSMs = 148;  // B200

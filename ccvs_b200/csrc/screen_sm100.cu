@@ -138,7 +138,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // ------------------------------------------------------------------------------------------------
 constexpr int BM = 128;            // latent rows per CTA tile (UMMA M)
 constexpr int BK = 64;             // dims per smem block (128 bytes of BF16 = one swizzle atom row)
-constexpr int RING = 8;            // candidate ring entries per (row, epilogue group)
+constexpr int LCAP = 12;           // candidate list entries per (row, epilogue group)
+constexpr uint32_t LSTRIDE = 128 * 8;   // bytes between consecutive entries of one row's list
 constexpr int SCREEN_THREADS = 384;
 constexpr int A_BLOCK_BYTES = BM * BK * 2;   // 16 KiB
 
@@ -151,8 +152,8 @@ __host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int BN, int n
   uint32_t off = 0;
   s.a = off;    off += (uint32_t)dblk * A_BLOCK_BYTES;
   s.b = off;    off += (uint32_t)nst * BN * BK * 2;
-  s.ring = off; off += 2u * RING * BM * 8;          // [group][slot][row] x {score, idx}
-  s.meta = off; off += 2u * BM * 16;                // [group][row] x {runmax, evicted, cnt, pad}
+  s.ring = off; off += 2u * LCAP * BM * 8;          // [group][slot][row] x {score, code}
+  s.meta = off; off += 2u * BM * 16;                // [group][row] x {runmax, overflow, count, pad}
   s.bias = off; off += 2u * 2u * BN * 4;            // [group][parity][BN]
   s.bars = off; off += 256;
   s.total = off;
@@ -272,8 +273,10 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const int row_in_tile = q * 32 + lane;
     const int tg = threadIdx.x - 128 - g * 128;   // 0..127 inside the group
     float* bias_s = reinterpret_cast<float*>(smem + lay.bias) + g * 2 * BN;
-    // ring entry (slot, row): {score, idx}
-    const uint32_t ring_base = smem_base + lay.ring + (uint32_t)(g * RING * BM + row_in_tile) * 8u;
+    // candidate list of (this row, this group): LCAP entries {score, code}, entry e at
+    // list_base + e*LSTRIDE (slot-major so that the 32 lanes of a warp hit 32 different banks)
+    const uint32_t list_base = smem_base + lay.ring + (uint32_t)(g * LCAP * BM + row_in_tile) * 8u;
+    const uint32_t list_end = list_base + LCAP * LSTRIDE;
     float* meta = reinterpret_cast<float*>(smem + lay.meta);
     uint32_t full_phase = 0;
     uint32_t it = 0;                           // tiles processed by this group (bias buffer parity)
@@ -281,8 +284,43 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     for (int tile = blockIdx.x; tile < num_row_tiles; tile += gridDim.x) {
       const int64_t row = (int64_t)tile * BM + row_in_tile;
       const float margin = __ldg(row_margin + row);
-      float runmax = -FLT_MAX, evicted = -FLT_MAX;
-      uint32_t cnt = 0;
+      float runmax = -FLT_MAX;
+      uint32_t lptr = list_base;               // next free list entry
+
+      // Drop entries that fell below the current threshold (they can no longer be within the margin
+      // of the row maximum).  If more than LCAP-4 survive, the lowest-scoring survivors are dropped
+      // and the best dropped score is remembered: the row is flagged at the end only if a dropped
+      // entry could still be inside the final margin.
+      float dropped_max = -FLT_MAX;
+      auto compact = [&](float thr) {
+        uint32_t w = list_base;
+        for (uint32_t r = list_base; r < lptr; r += LSTRIDE) {
+          float sc;
+          uint32_t code;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(sc), "=r"(code) : "r"(r));
+          if (sc >= thr) {
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(w), "f"(sc), "r"(code) : "memory");
+            w += LSTRIDE;
+          }
+        }
+        while (w > list_end - 4 * LSTRIDE) {
+          float lo = INFINITY;             // victim: lowest score, highest code among equals
+          uint32_t lo_code = 0, lo_at = list_base;
+          for (uint32_t r = list_base; r < w; r += LSTRIDE) {
+            float sc;
+            uint32_t code;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(sc), "=r"(code) : "r"(r));
+            if (sc < lo || (sc == lo && code > lo_code)) { lo = sc; lo_code = code; lo_at = r; }
+          }
+          dropped_max = fmaxf(dropped_max, lo);
+          w -= LSTRIDE;                       // move the last entry into the hole
+          float sc;
+          uint32_t code;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(sc), "=r"(code) : "r"(w));
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(lo_at), "f"(sc), "r"(code) : "memory");
+        }
+        lptr = w;
+      };
 
       float nb[BN / 128];
       if (g < num_n_tiles) {
@@ -304,6 +342,10 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
         const int col0 = j * BN;
 
+        // One 32-column chunk of this thread's row.  Fast path: bias add + max tree (FMNMX3).  A
+        // chunk can only contribute candidates if its maximum reaches (running max - margin); then
+        // the threshold is refreshed and each group of 4 columns that reaches it is appended with
+        // predicated (branch-free) stores.
         auto process = [&](uint32_t (&r)[32], int cbase) {
           float v[32];
           const float4* b4 = reinterpret_cast<const float4*>(bs + cbase);
@@ -319,82 +361,84 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 32; ++i) dbg_scores[row * K_pad + col0 + cbase + i] = v[i];
           }
-          float m = v[0];
+          float m4[8];
 #pragma unroll
-          for (int i = 1; i < 32; ++i) m = fmaxf(m, v[i]);
+          for (int i = 0; i < 8; ++i)
+            m4[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
+          const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
+                                fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
           if (m >= runmax - margin) {
             runmax = fmaxf(runmax, m);
             const float thr = runmax - margin;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (v[i] >= thr) {
-                const uint32_t addr = ring_base + (cnt & (RING - 1)) * (BM * 8u);
-                if (cnt >= RING) {
-                  float old;
-                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(old) : "r"(addr));
-                  evicted = fmaxf(evicted, old);
+            for (int i = 0; i < 8; ++i) {
+              if (m4[i] >= thr) {
+                if (lptr > list_end - 4 * LSTRIDE) compact(thr);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  asm volatile(
+                      "{\n\t"
+                      ".reg .pred p;\n\t"
+                      "setp.ge.f32 p, %1, %2;\n\t"
+                      "@p st.shared.v2.b32 [%0], {%1, %3};\n\t"
+                      "@p add.u32 %0, %0, %4;\n\t"
+                      "}"
+                      : "+r"(lptr)
+                      : "f"(v[4 * i + u]), "f"(thr), "r"((uint32_t)(col0 + cbase + 4 * i + u)), "n"(LSTRIDE)
+                      : "memory");
                 }
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(__float_as_uint(v[i])),
-                             "r"((uint32_t)(col0 + cbase + i))
-                             : "memory");
-                ++cnt;
               }
             }
           }
         };
 
-        uint32_t ra[32], rb[32];
-        tmem_ld32(taddr0, ra);
+        // (the sibling epilogue group's warp on the same SM sub-partition covers the tcgen05.ld latency)
+        uint32_t ra[32];
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; c += 2) {
+        for (int c = 0; c < BN / 32; ++c) {
+          tmem_ld32(taddr0 + c * 32, ra);
           tmem_ld_wait();
-          tmem_ld32(taddr0 + (c + 1) * 32, rb);
           process(ra, c * 32);
-          tmem_ld_wait();
-          if (c + 2 < BN / 32) tmem_ld32(taddr0 + (c + 2) * 32, ra);
-          process(rb, (c + 1) * 32);
         }
         tc_fence_before();
         mbar_arrive(tmem_empty(g));
       }
 
-      // ---- merge the two groups' rings for this row tile
+      // ---- merge the two groups' lists for this row tile
       meta[(g * BM + row_in_tile) * 4 + 0] = runmax;
-      meta[(g * BM + row_in_tile) * 4 + 1] = evicted;
-      meta[(g * BM + row_in_tile) * 4 + 2] = __uint_as_float(cnt);
+      meta[(g * BM + row_in_tile) * 4 + 1] = dropped_max;
+      meta[(g * BM + row_in_tile) * 4 + 2] = __uint_as_float((lptr - list_base) / LSTRIDE);
       named_bar_sync(1, 256);
       if (g == 0) {
         const float om = meta[(BM + row_in_tile) * 4 + 0];
-        const float oe = meta[(BM + row_in_tile) * 4 + 1];
-        const uint32_t oc = __float_as_uint(meta[(BM + row_in_tile) * 4 + 2]);
-        const float fmax_ = fmaxf(runmax, om);
-        const float thr = fmax_ - margin;
-        const uint32_t n0 = cnt < RING ? cnt : RING, n1 = oc < RING ? oc : RING;
-        const float2* ring0 =
-            reinterpret_cast<const float2*>(smem + lay.ring) + row_in_tile;            // group 0
-        const float2* ring1 = ring0 + RING * BM;                                        // group 1
-        bool overflow = fmaxf(evicted, oe) >= thr;
-        // selection: repeatedly take the best entry strictly after the previous pick in
-        // (score desc, idx asc) order
-        float prev_s = INFINITY;
-        int prev_i = -1;
-        int written = 0;
+        const float od = meta[(BM + row_in_tile) * 4 + 1];
+        const uint32_t n1 = __float_as_uint(meta[(BM + row_in_tile) * 4 + 2]);
+        const uint32_t n0 = (lptr - list_base) / LSTRIDE;
+        const float thr = fmaxf(runmax, om) - margin;
+        const float2* l0 = reinterpret_cast<const float2*>(smem + lay.ring) + row_in_tile;   // group 0
+        const float2* l1 = l0 + LCAP * BM;                                                    // group 1
+        bool overflow = fmaxf(dropped_max, od) >= thr;
         uint32_t within = 0;
-        for (uint32_t e = 0; e < n0; ++e) within += (ring0[e * BM].x >= thr);
-        for (uint32_t e = 0; e < n1; ++e) within += (ring1[e * BM].x >= thr);
+        for (uint32_t e = 0; e < n0; ++e) within += (l0[e * BM].x >= thr);
+        for (uint32_t e = 0; e < n1; ++e) within += (l1[e * BM].x >= thr);
         if (within > (uint32_t)n_cand) overflow = true;
         if (row < N) {
+          // selection: repeatedly take the best entry strictly after the previous pick in
+          // (score desc, code asc) order
+          float prev_s = INFINITY;
+          int prev_i = -1;
+          int written = 0;
           for (int c = 0; c < n_cand; ++c) {
             float bs_ = -INFINITY;
             int bi = 0x7fffffff;
             for (uint32_t e = 0; e < n0 + n1; ++e) {
-              const float2 ent = (e < n0) ? ring0[e * BM] : ring1[(e - n0) * BM];
-              const float s = ent.x;
+              const float2 ent = (e < n0) ? l0[e * BM] : l1[(e - n0) * BM];
+              const float sc = ent.x;
               const int i = (int)__float_as_uint(ent.y);
-              if (!(s >= thr) || i >= K) continue;
-              const bool after_prev = (s < prev_s) || (s == prev_s && i > prev_i);
-              const bool better = (s > bs_) || (s == bs_ && i < bi);
-              if (after_prev && better) { bs_ = s; bi = i; }
+              if (!(sc >= thr) || i >= K) continue;
+              const bool after_prev = (sc < prev_s) || (sc == prev_s && i > prev_i);
+              const bool better = (sc > bs_) || (sc == bs_ && i < bi);
+              if (after_prev && better) { bs_ = sc; bi = i; }
             }
             if (bi == 0x7fffffff) break;
             cand_idx[row * n_cand + c] = bi;

@@ -19,11 +19,24 @@ constexpr int XC = 64;    // codes per slab
 constexpr int XK = 16;    // dims per slab
 constexpr int XT = 256;   // threads
 
+// order-preserving map float -> uint32, packed with the code so that a 64-bit unsigned minimum is the
+// lexicographic (distance, code) minimum, i.e. the first-occurrence argmin
+__device__ __forceinline__ unsigned long long pack_key(float d, int k) {
+  uint32_t b = __float_as_uint(d);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)b << 32) | (uint32_t)k;
+}
+
+// row_list == nullptr: all L.N rows, one K sweep per CTA, indices written directly.
+// row_list != nullptr: only the listed rows (count on the device); blockIdx.y selects a slice of the
+//   codebook, partial results meet in keys[] via 64-bit atomicMin and the last CTA to finish turns
+//   the keys into indices (single launch, no host sync).
 __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restrict__ z, Lay L,
                                                           const float* __restrict__ E,
                                                           const float* __restrict__ e_sq, int K,
                                                           const int64_t* __restrict__ row_list,
-                                                          const int32_t* __restrict__ row_count,
+                                                          unsigned long long* __restrict__ keys,
+                                                          int32_t* __restrict__ row_count,
                                                           int64_t max_rows, int64_t* __restrict__ idx) {
   extern __shared__ float smem[];
   const int Dp = ((L.D + XK - 1) / XK) * XK;      // D padded to the slab depth
@@ -34,9 +47,13 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
   int* red_k = reinterpret_cast<int*>(red_d + XR * 16);   // [XR][16]
   __shared__ int64_t row_id[XR];
 
-  const int64_t total_rows = row_list ? min((int64_t)__ldg(row_count), max_rows) : L.N;
+  const int64_t total_rows = row_list ? min((int64_t)row_count[0], max_rows) : L.N;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
+  // this CTA's slice of the codebook (whole codebook when gridDim.y == 1), aligned to the slab width
+  const int slice = ((K + (int)gridDim.y - 1) / (int)gridDim.y + XC - 1) / XC * XC;
+  const int k_begin = (int)blockIdx.y * slice;
+  const int k_end = min(K, k_begin + slice);
 
   for (int64_t r0 = (int64_t)blockIdx.x * XR; r0 < total_rows; r0 += (int64_t)gridDim.x * XR) {
     const int nr = (int)min((int64_t)XR, total_rows - r0);
@@ -81,7 +98,7 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
 #pragma unroll
     for (int i = 0; i < 4; ++i) { best_d[i] = INFINITY; best_k[i] = 0x7fffffff; }
 
-    for (int k0 = 0; k0 < K; k0 += XC) {
+    for (int k0 = k_begin; k0 < k_end; k0 += XC) {
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -98,7 +115,7 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
           for (int u = 0; u < 4; ++u) {
             const int j = j0 + jq + u;
             float v = 0.f;
-            if (k < K && j < L.D) v = __ldg(E + (size_t)k * L.D + j);
+            if (k < k_end && j < L.D) v = __ldg(E + (size_t)k * L.D + j);
             es[(jq + u) * XC + code] = v;
           }
         }
@@ -119,7 +136,7 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int k = k0 + tx * 4 + c;
-        if (k < K) {
+        if (k < k_end) {
           const float ee = __ldg(e_sq + k);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -144,7 +161,26 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
         const int k = red_k[tid * 16 + t];
         if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
       }
-      idx[row_id[tid]] = (bk == 0x7fffffff) ? 0 : bk;
+      if (row_list) {
+        if (bk != 0x7fffffff) atomicMin(keys + r0 + tid, pack_key(bd, bk));
+      } else {
+        idx[row_id[tid]] = (bk == 0x7fffffff) ? 0 : bk;
+      }
+    }
+  }
+  if (row_list) {
+    // last CTA to finish converts the packed keys of all listed rows into plain indices
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(row_count + 1, 1) == (int)(gridDim.x * gridDim.y) - 1);
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      for (int64_t i = tid; i < total_rows; i += XT) {
+        const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(keys + i);
+        idx[row_list[i]] = (int64_t)(key & 0xffffffffull);
+      }
     }
   }
 }
@@ -155,19 +191,28 @@ static size_t exact_smem_bytes(int D) {
 }
 
 static int launch_exact(const float* z, const Lay& L, const float* E, const float* e_sq, int K,
-                        const int64_t* rows, const int32_t* row_count, int64_t max_rows, int64_t* idx,
-                        cudaStream_t st) {
+                        const int64_t* rows, unsigned long long* keys, int32_t* row_count,
+                        int64_t max_rows, int64_t* idx, cudaStream_t st) {
   const size_t smem = exact_smem_bytes(L.D);
   CCVSQ_REQUIRE(smem <= 227 * 1024, CCVSQ_UNSUPPORTED,
                 "search_exact: D=%d needs %zu bytes of shared memory (> 227 KiB)", L.D, smem);
   if (int rc = enable_smem(search_exact_kernel, smem)) return rc;
   const int64_t work = rows ? max_rows : L.N;
   int64_t blocks = (work + XR - 1) / XR;
-  const int64_t cap = (int64_t)kNumSMs * 16;
-  if (blocks > cap) blocks = cap;
+  int slices = 1;
+  if (rows) {
+    // few rows, possibly a large codebook: split K so that a handful of rows still fills the chip
+    slices = (K + 1023) / 1024;
+    if (slices > 16) slices = 16;
+    const int64_t cap = (4 * kNumSMs) / slices;
+    if (blocks > cap) blocks = cap;
+  } else {
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+  }
   if (blocks < 1) blocks = 1;
-  search_exact_kernel<<<(unsigned)blocks, XT, smem, st>>>(z, L, E, e_sq, K, rows, row_count, max_rows,
-                                                        idx);
+  search_exact_kernel<<<dim3((unsigned)blocks, slices), XT, smem, st>>>(z, L, E, e_sq, K, rows, keys,
+                                                                      row_count, max_rows, idx);
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
 }
@@ -182,19 +227,21 @@ extern "C" int ccvsq_search_exact(const float* z, ccvsq_layout lay, const float*
   CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "search_exact: K=%d", K);
   Lay L;
   if (int rc = make_lay(lay, &L)) return rc;
-  return launch_exact(z, L, E, e_sq, K, nullptr, nullptr, 0, idx, (cudaStream_t)stream);
+  return launch_exact(z, L, E, e_sq, K, nullptr, nullptr, nullptr, 0, idx, (cudaStream_t)stream);
 }
 
 extern "C" int ccvsq_search_exact_rows(const float* z, ccvsq_layout lay, const float* E,
-                                       const float* e_sq, int K, const int64_t* rows,
-                                       const int32_t* row_count, int64_t max_rows, int64_t* idx,
+                                       const float* e_sq, int K, int64_t* fallback_ws,
+                                       int32_t* fallback_count, int64_t fallback_capacity, int64_t* idx,
                                        void* stream) {
-  CCVSQ_REQUIRE(z && E && e_sq && idx && rows && row_count, CCVSQ_NULL_POINTER,
+  CCVSQ_REQUIRE(z && E && e_sq && idx && fallback_ws && fallback_count, CCVSQ_NULL_POINTER,
                 "search_exact_rows: null pointer");
-  CCVSQ_REQUIRE(K > 0 && max_rows >= 0, CCVSQ_BAD_SHAPE, "search_exact_rows: K=%d max_rows=%lld", K,
-                (long long)max_rows);
-  if (max_rows == 0) return CCVSQ_OK;
+  CCVSQ_REQUIRE(K > 0 && fallback_capacity >= 0, CCVSQ_BAD_SHAPE, "search_exact_rows: K=%d capacity=%lld",
+                K, (long long)fallback_capacity);
+  if (fallback_capacity == 0) return CCVSQ_OK;
   Lay L;
   if (int rc = make_lay(lay, &L)) return rc;
-  return launch_exact(z, L, E, e_sq, K, rows, row_count, max_rows, idx, (cudaStream_t)stream);
+  return launch_exact(z, L, E, e_sq, K, fallback_ws,
+                      reinterpret_cast<unsigned long long*>(fallback_ws + fallback_capacity), fallback_count,
+                      fallback_capacity, idx, (cudaStream_t)stream);
 }

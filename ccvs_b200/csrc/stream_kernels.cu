@@ -186,7 +186,10 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const float* __restrict__ z
     else idx[n] = c0;
     if (flags && (flags[n] & 1) && fb_rows) {
       int slot = atomicAdd(fb_count, 1);
-      if (slot < fb_cap) fb_rows[slot] = n;
+      if (slot < fb_cap) {
+        fb_rows[slot] = n;
+        fb_rows[fb_cap + slot] = -1;     // packed (distance, code) key, all ones = +inf
+      }
     }
   }
   __syncthreads();

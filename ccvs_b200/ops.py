@@ -218,8 +218,8 @@ def rescore(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, sr: ScreenResult
     cap = 0
     if exact_fallback:
         cap = min(N, fallback_capacity)
-        fb_rows = torch.empty(cap, dtype=torch.int64, device=dev)
-        fb_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        fb_rows = torch.empty(2 * cap, dtype=torch.int64, device=dev)     # rows | packed keys
+        fb_count = torch.zeros(2, dtype=torch.int32, device=dev)          # queued rows, scratch counter
     _call("ccvsq_rescore", _ptr(z), lay, _ptr(cb.weight), _ptr(cb.e_sq), cb.K, _ptr(sr.cand_idx), n_cand,
                          _ptr(sr.flags), _ptr(idx), _ptr(fb_rows), _ptr(fb_count), cap, _stream(dev))
     if exact_fallback:

@@ -108,17 +108,21 @@ int ccvsq_screen_dump(const void* z_bf16, const float* row_margin, const void* E
 
 /* ccvsq_rescore: FP32 re-evaluation of the screened candidates with the reference's formula and
  * lowest-index tie-break (quantize.py:45-50); rows with a single candidate take it directly.
- * Rows whose flags bit0 is set are appended to fallback_rows[0..fallback_capacity) and counted in
- * *fallback_count (caller zeroes it; both may be NULL to ignore overflow).                     */
+ * Rows whose flags bit0 is set are queued for the exact fallback:
+ *   fallback_ws    int64 [2*fallback_capacity]: row numbers, then packed (distance, code) keys
+ *   fallback_count int32 [2], zeroed by the caller: [0] rows queued, [1] scratch counter
+ * (both may be NULL to ignore overflow rows).                                                   */
 int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, const float* e_sq, int K,
                   const int32_t* cand_idx, int n_cand, const uint8_t* flags, int64_t* idx,
-                  int64_t* fallback_rows, int32_t* fallback_count, int64_t fallback_capacity,
+                  int64_t* fallback_ws, int32_t* fallback_count, int64_t fallback_capacity,
                   void* stream);
 
-/* Exact search restricted to the listed rows (count read on the device, no host sync).        */
+/* Exact FP32 search restricted to the rows queued by ccvsq_rescore (count read on the device, no
+ * host sync).  The codebook is split across CTAs, partial minima meet through 64-bit atomicMin on
+ * the packed keys, the last CTA writes idx[row].                                                */
 int ccvsq_search_exact_rows(const float* z, ccvsq_layout lay, const float* E, const float* e_sq,
-                            int K, const int64_t* rows, const int32_t* row_count, int64_t max_rows,
-                            int64_t* idx, void* stream);
+                            int K, int64_t* fallback_ws, int32_t* fallback_count,
+                            int64_t fallback_capacity, int64_t* idx, void* stream);
 
 /* ---- assignment: gather + straight-through value + squared error ---------------------------
  * Replaces quantize.py:55 (one-hot GEMM == E[idx]), :60-61 (loss numerator) and :64 (STE value).
