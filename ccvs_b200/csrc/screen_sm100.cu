@@ -138,26 +138,74 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // ------------------------------------------------------------------------------------------------
 constexpr int BM = 128;            // latent rows per CTA tile (UMMA M)
 constexpr int BK = 64;             // dims per smem block (128 bytes of BF16 = one swizzle atom row)
-constexpr int LCAP = 12;           // candidate list entries per (row, epilogue group)
-constexpr uint32_t LSTRIDE = 128 * 8;   // bytes between consecutive entries of one row's list
+constexpr int LCAP = 6;                 // candidate-list entries per (row, epilogue group)
+constexpr uint32_t SC_STRIDE = 128 * 16;   // entry e of a row: 4 raw scores at sc_base + e*SC_STRIDE ...
+constexpr uint32_t CO_STRIDE = 128 * 4;    // ... and the first code of the group at co_base + e*CO_STRIDE
+constexpr uint32_t LIST_BYTES = LCAP * (SC_STRIDE + CO_STRIDE);   // per epilogue group
 constexpr int SCREEN_THREADS = 384;
 constexpr int A_BLOCK_BYTES = BM * BK * 2;   // 16 KiB
 
 struct ScreenSmem {
   // byte offsets inside the 1024-aligned dynamic shared memory
-  uint32_t a, b, ring, meta, bias, bars, total;
+  uint32_t a, b, ring, bias, bars, total;
 };
 __host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int BN, int nst) {
   ScreenSmem s;
   uint32_t off = 0;
   s.a = off;    off += (uint32_t)dblk * A_BLOCK_BYTES;
   s.b = off;    off += (uint32_t)nst * BN * BK * 2;
-  s.ring = off; off += 2u * LCAP * BM * 8;          // [group][slot][row] x {score, code}
-  s.meta = off; off += 2u * BM * 16;                // [group][row] x {runmax, overflow, count, pad}
+  s.ring = off; off += 2u * LIST_BYTES;             // [group]{ [slot][row] float4 | [slot][row] u32 }
   s.bias = off; off += 2u * 2u * BN * 4;            // [group][parity][BN]
   s.bars = off; off += 256;
   s.total = off;
   return s;
+}
+
+// Candidate list maintenance (rare path).  Drops entries whose best score fell below `thr`; if
+// more than LCAP-2 survive, the entries with the lowest best score go too and the best dropped
+// score is remembered, so the row is flagged only if a dropped code could still be inside the
+// final margin.
+__device__ __noinline__ void list_compact(uint32_t sc_base, uint32_t co_base, uint32_t& psc, uint32_t& pco,
+                                          float thr, float& dropped_max) {
+  const uint32_t n = (pco - co_base) / CO_STRIDE;
+  uint32_t w = 0;
+  for (uint32_t e = 0; e < n; ++e) {
+    float a, b, c, d;
+    uint32_t code;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(sc_base + e * SC_STRIDE));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
+    if (fmaxf(fmaxf(a, b), fmaxf(c, d)) >= thr) {
+      if (w != e) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sc_base + w * SC_STRIDE), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(co_base + w * CO_STRIDE), "r"(code) : "memory");
+      }
+      ++w;
+    }
+  }
+  while (w > LCAP - 2) {
+    float lo = INFINITY;              // victim: lowest best score, highest code among equals
+    uint32_t lo_code = 0, lo_e = 0;
+    for (uint32_t e = 0; e < w; ++e) {
+      float a, b, c, d;
+      uint32_t code;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(sc_base + e * SC_STRIDE));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
+      const float mx = fmaxf(fmaxf(a, b), fmaxf(c, d));
+      if (mx < lo || (mx == lo && code > lo_code)) { lo = mx; lo_code = code; lo_e = e; }
+    }
+    dropped_max = fmaxf(dropped_max, lo);
+    --w;
+    if (lo_e != w) {                  // move the last entry into the hole
+      float a, b, c, d;
+      uint32_t code;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(sc_base + w * SC_STRIDE));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + w * CO_STRIDE));
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sc_base + lo_e * SC_STRIDE), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(co_base + lo_e * CO_STRIDE), "r"(code) : "memory");
+    }
+  }
+  psc = sc_base + w * SC_STRIDE;
+  pco = co_base + w * CO_STRIDE;
 }
 
 template <int BN, int NST>
@@ -183,7 +231,8 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   const uint32_t a_empty = bar0 + 8u * (2 * NST + 1);
   auto tmem_full = [&](int b) { return bar0 + 8u * (2 * NST + 2 + b); };
   auto tmem_empty = [&](int b) { return bar0 + 8u * (2 * NST + 4 + b); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + lay.bars + 8u * (2 * NST + 6));
+  auto bias_rdy = [&](int g) { return bar0 + 8u * (2 * NST + 6 + g); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + lay.bars + 8u * (2 * NST + 8));
 
   if ((smem_base & 1023u) != 0) __trap();   // SWIZZLE_128B needs 1024-byte aligned tiles
 
@@ -195,7 +244,11 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 128); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full(b), 1);
+      mbar_init(tmem_empty(b), 128);
+      mbar_init(bias_rdy(b), 128);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -268,94 +321,69 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     }
   } else if (warp >= 4) {
     // =========================== epilogue groups ===========================
+    // The two groups are fully decoupled: group g owns the code tiles j == g (mod 2) and the TMEM
+    // buffer g, keeps its own running maximum and candidate list and writes its own half of the
+    // output; ccvsq_rescore merges the two halves.
     const int g = (warp - 4) >> 2;             // 0: even code tiles, 1: odd code tiles
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int row_in_tile = q * 32 + lane;
     const int tg = threadIdx.x - 128 - g * 128;   // 0..127 inside the group
     float* bias_s = reinterpret_cast<float*>(smem + lay.bias) + g * 2 * BN;
-    // candidate list of (this row, this group): LCAP entries {score, code}, entry e at
-    // list_base + e*LSTRIDE (slot-major so that the 32 lanes of a warp hit 32 different banks)
-    const uint32_t list_base = smem_base + lay.ring + (uint32_t)(g * LCAP * BM + row_in_tile) * 8u;
-    const uint32_t list_end = list_base + LCAP * LSTRIDE;
-    float* meta = reinterpret_cast<float*>(smem + lay.meta);
+    const uint32_t sc_base = smem_base + lay.ring + (uint32_t)g * LIST_BYTES + (uint32_t)row_in_tile * 16u;
+    const uint32_t co_base = smem_base + lay.ring + (uint32_t)g * LIST_BYTES + LCAP * SC_STRIDE + (uint32_t)row_in_tile * 4u;
+    const uint32_t co_limit = co_base + (LCAP - 2) * CO_STRIDE;   // appending 2 groups needs pco <= co_limit
     uint32_t full_phase = 0;
     uint32_t it = 0;                           // tiles processed by this group (bias buffer parity)
+    const bool has_tiles = g < num_n_tiles;
+
+    // bias of the next tile this group will process, prefetched one tile ahead (also across row tiles)
+    float nb[BN / 128];
+    if (has_tiles && (int)blockIdx.x < num_row_tiles) {
+#pragma unroll
+      for (int u = 0; u < BN / 128; ++u) nb[u] = __ldg(bias + (size_t)g * BN + u * 128 + tg);
+    }
 
     for (int tile = blockIdx.x; tile < num_row_tiles; tile += gridDim.x) {
       const int64_t row = (int64_t)tile * BM + row_in_tile;
       const float margin = __ldg(row_margin + row);
       float runmax = -FLT_MAX;
-      uint32_t lptr = list_base;               // next free list entry
-
-      // Drop entries that fell below the current threshold (they can no longer be within the margin
-      // of the row maximum).  If more than LCAP-4 survive, the lowest-scoring survivors are dropped
-      // and the best dropped score is remembered: the row is flagged at the end only if a dropped
-      // entry could still be inside the final margin.
       float dropped_max = -FLT_MAX;
-      auto compact = [&](float thr) {
-        uint32_t w = list_base;
-        for (uint32_t r = list_base; r < lptr; r += LSTRIDE) {
-          float sc;
-          uint32_t code;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(sc), "=r"(code) : "r"(r));
-          if (sc >= thr) {
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(w), "f"(sc), "r"(code) : "memory");
-            w += LSTRIDE;
-          }
-        }
-        while (w > list_end - 4 * LSTRIDE) {
-          float lo = INFINITY;             // victim: lowest score, highest code among equals
-          uint32_t lo_code = 0, lo_at = list_base;
-          for (uint32_t r = list_base; r < w; r += LSTRIDE) {
-            float sc;
-            uint32_t code;
-            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(sc), "=r"(code) : "r"(r));
-            if (sc < lo || (sc == lo && code > lo_code)) { lo = sc; lo_code = code; lo_at = r; }
-          }
-          dropped_max = fmaxf(dropped_max, lo);
-          w -= LSTRIDE;                       // move the last entry into the hole
-          float sc;
-          uint32_t code;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(sc), "=r"(code) : "r"(w));
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(lo_at), "f"(sc), "r"(code) : "memory");
-        }
-        lptr = w;
-      };
+      uint32_t psc = sc_base, pco = co_base;    // next free list entry
 
-      float nb[BN / 128];
-      if (g < num_n_tiles) {
-#pragma unroll
-        for (int u = 0; u < BN / 128; ++u) nb[u] = __ldg(bias + (size_t)g * BN + u * 128 + tg);
-      }
       for (int j = g; j < num_n_tiles; j += 2, ++it) {
         float* bs = bias_s + (it & 1) * BN;
 #pragma unroll
         for (int u = 0; u < BN / 128; ++u) bs[u * 128 + tg] = nb[u];
-        named_bar_sync(3 + g, 128);
-        if (j + 2 < num_n_tiles) {
+        mbar_arrive(bias_rdy(g));               // (waited on below, after the accumulator wait)
+        {
+          int jn = j + 2;                       // next tile of this group: same row tile, or the
+          if (jn >= num_n_tiles) jn = g;        // first one of the next row tile
+          if (j + 2 < num_n_tiles || tile + (int)gridDim.x < num_row_tiles) {
 #pragma unroll
-          for (int u = 0; u < BN / 128; ++u) nb[u] = __ldg(bias + (size_t)(j + 2) * BN + u * 128 + tg);
+            for (int u = 0; u < BN / 128; ++u) nb[u] = __ldg(bias + (size_t)jn * BN + u * 128 + tg);
+          }
         }
         mbar_wait(tmem_full(g), full_phase);
         full_phase ^= 1;
         tc_fence_after();
+        mbar_wait(bias_rdy(g), it & 1);         // all 128 threads of the group stored their bias slice
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
         const int col0 = j * BN;
 
         // One 32-column chunk of this thread's row.  Fast path: bias add + max tree (FMNMX3).  A
         // chunk can only contribute candidates if its maximum reaches (running max - margin); then
-        // the threshold is refreshed and each group of 4 columns that reaches it is appended with
-        // predicated (branch-free) stores.
-        auto process = [&](uint32_t (&r)[32], int cbase) {
+        // the threshold is refreshed and every group of 4 columns whose maximum reaches it is
+        // appended (its 4 raw scores + first code) with predicated, branch-free stores.
+        auto process = [&](uint32_t (&ra)[32], const int cbase) {
           float v[32];
           const float4* b4 = reinterpret_cast<const float4*>(bs + cbase);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bb = b4[i];
-            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
-            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
-            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
-            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+            v[4 * i + 0] = __uint_as_float(ra[4 * i + 0]) + bb.x;
+            v[4 * i + 1] = __uint_as_float(ra[4 * i + 1]) + bb.y;
+            v[4 * i + 2] = __uint_as_float(ra[4 * i + 2]) + bb.z;
+            v[4 * i + 3] = __uint_as_float(ra[4 * i + 3]) + bb.w;
           }
           if (dbg_scores) {   // diagnostic dump of the raw score tile (ccvsq_screen_dump only)
 #pragma unroll
@@ -368,93 +396,112 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
                                 fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
           if (m >= runmax - margin) {
+            // a maximum that beats the old one by more than the margin makes every listed entry stale
+            if (m > runmax + margin) { psc = sc_base; pco = co_base; }
             runmax = fmaxf(runmax, m);
             const float thr = runmax - margin;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (m4[i] >= thr) {
-                if (lptr > list_end - 4 * LSTRIDE) compact(thr);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  asm volatile(
-                      "{\n\t"
-                      ".reg .pred p;\n\t"
-                      "setp.ge.f32 p, %1, %2;\n\t"
-                      "@p st.shared.v2.b32 [%0], {%1, %3};\n\t"
-                      "@p add.u32 %0, %0, %4;\n\t"
-                      "}"
-                      : "+r"(lptr)
-                      : "f"(v[4 * i + u]), "f"(thr), "r"((uint32_t)(col0 + cbase + 4 * i + u)), "n"(LSTRIDE)
-                      : "memory");
-                }
+              if ((i & 1) == 0) {
+                if (pco > co_limit) list_compact(sc_base, co_base, psc, pco, thr, dropped_max);
               }
+              asm volatile(
+                  "{\n\t"
+                  ".reg .pred p;\n\t"
+                  "setp.ge.f32 p, %2, %3;\n\t"
+                  "@p st.shared.v4.f32 [%0], {%4, %5, %6, %7};\n\t"
+                  "@p st.shared.u32 [%1], %8;\n\t"
+                  "@p add.u32 %0, %0, %9;\n\t"
+                  "@p add.u32 %1, %1, %10;\n\t"
+                  "}"
+                  : "+r"(psc), "+r"(pco)
+                  : "f"(m4[i]), "f"(thr), "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]),
+                    "r"((uint32_t)(col0 + cbase + 4 * i)), "n"(SC_STRIDE), "n"(CO_STRIDE)
+                  : "memory");
             }
           }
         };
 
-        // (the sibling epilogue group's warp on the same SM sub-partition covers the tcgen05.ld latency)
-        uint32_t ra[32];
+        // two 32-column chunks in flight: the tcgen05.ld of chunk c+1 overlaps the arithmetic on chunk c
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr0, ra);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          tmem_ld32(taddr0 + c * 32, ra);
+        for (int c = 0; c < BN / 32; c += 2) {
           tmem_ld_wait();
+          tmem_ld32(taddr0 + (c + 1) * 32, rb);
           process(ra, c * 32);
+          tmem_ld_wait();
+          if (c + 2 < BN / 32) tmem_ld32(taddr0 + (c + 2) * 32, ra);
+          process(rb, (c + 1) * 32);
         }
         tc_fence_before();
         mbar_arrive(tmem_empty(g));
       }
 
-      // ---- merge the two groups' lists for this row tile
-      meta[(g * BM + row_in_tile) * 4 + 0] = runmax;
-      meta[(g * BM + row_in_tile) * 4 + 1] = dropped_max;
-      meta[(g * BM + row_in_tile) * 4 + 2] = __uint_as_float((lptr - list_base) / LSTRIDE);
-      named_bar_sync(1, 256);
-      if (g == 0) {
-        const float om = meta[(BM + row_in_tile) * 4 + 0];
-        const float od = meta[(BM + row_in_tile) * 4 + 1];
-        const uint32_t n1 = __float_as_uint(meta[(BM + row_in_tile) * 4 + 2]);
-        const uint32_t n0 = (lptr - list_base) / LSTRIDE;
-        const float thr = fmaxf(runmax, om) - margin;
-        const float2* l0 = reinterpret_cast<const float2*>(smem + lay.ring) + row_in_tile;   // group 0
-        const float2* l1 = l0 + LCAP * BM;                                                    // group 1
-        bool overflow = fmaxf(dropped_max, od) >= thr;
+      // ---- this group's candidates for the row: every listed code with score >= runmax - margin,
+      //      sorted by (score desc, code asc), at most n_cand of them
+      if (row < N) {
+        const int64_t obase = (row * 2 + g) * n_cand;
+        const float thr = runmax - margin;
+        const uint32_t n = (pco - co_base) / CO_STRIDE;
         uint32_t within = 0;
-        for (uint32_t e = 0; e < n0; ++e) within += (l0[e * BM].x >= thr);
-        for (uint32_t e = 0; e < n1; ++e) within += (l1[e * BM].x >= thr);
-        if (within > (uint32_t)n_cand) overflow = true;
-        if (row < N) {
-          // selection: repeatedly take the best entry strictly after the previous pick in
-          // (score desc, code asc) order
-          float prev_s = INFINITY;
-          int prev_i = -1;
-          int written = 0;
-          for (int c = 0; c < n_cand; ++c) {
+        float best_s = -INFINITY;
+        int best_i = 0x7fffffff;
+        for (uint32_t e = 0; e < n; ++e) {
+          float sc[4];
+          uint32_t code;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = (int)code + u;
+            if (sc[u] >= thr && i < K) {
+              ++within;
+              if (sc[u] > best_s || (sc[u] == best_s && i < best_i)) { best_s = sc[u]; best_i = i; }
+            }
+          }
+        }
+        int written = 0;
+        if (within >= 1) {
+          cand_idx[obase] = best_i;
+          cand_score[obase] = best_s;
+          written = 1;
+        }
+        if (within > 1) {          // rare: near-ties; repeated selection in (score desc, code asc) order
+          float prev_s = best_s;
+          int prev_i = best_i;
+          for (int c = 1; c < n_cand; ++c) {
             float bs_ = -INFINITY;
             int bi = 0x7fffffff;
-            for (uint32_t e = 0; e < n0 + n1; ++e) {
-              const float2 ent = (e < n0) ? l0[e * BM] : l1[(e - n0) * BM];
-              const float sc = ent.x;
-              const int i = (int)__float_as_uint(ent.y);
-              if (!(sc >= thr) || i >= K) continue;
-              const bool after_prev = (sc < prev_s) || (sc == prev_s && i > prev_i);
-              const bool better = (sc > bs_) || (sc == bs_ && i < bi);
-              if (after_prev && better) { bs_ = sc; bi = i; }
+            for (uint32_t e = 0; e < n; ++e) {
+              float sc[4];
+              uint32_t code;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = (int)code + u;
+                const float x = sc[u];
+                if (!(x >= thr) || i >= K) continue;
+                const bool after_prev = (x < prev_s) || (x == prev_s && i > prev_i);
+                const bool better = (x > bs_) || (x == bs_ && i < bi);
+                if (after_prev && better) { bs_ = x; bi = i; }
+              }
             }
             if (bi == 0x7fffffff) break;
-            cand_idx[row * n_cand + c] = bi;
-            cand_score[row * n_cand + c] = bs_;
+            cand_idx[obase + c] = bi;
+            cand_score[obase + c] = bs_;
             prev_s = bs_;
             prev_i = bi;
             ++written;
           }
-          for (int c = written; c < n_cand; ++c) {
-            cand_idx[row * n_cand + c] = -1;
-            cand_score[row * n_cand + c] = -INFINITY;
-          }
-          flags[row] = overflow ? 1 : 0;
         }
+        for (int c = written; c < n_cand; ++c) {
+          cand_idx[obase + c] = -1;
+          cand_score[obase + c] = -INFINITY;
+        }
+        flags[row * 2 + g] = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped_max >= thr ? 2 : 0));
       }
-      named_bar_sync(2, 256);
     }
   }
 

@@ -156,12 +156,16 @@ __global__ void __launch_bounds__(NT) pack_latents_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// rescore: FP32 re-evaluation of screened candidates (reference formula, lowest-index ties)
+// rescore: merge the two epilogue groups' candidate lists, then FP32 re-evaluation of the survivors
+// (reference formula, lowest-index ties).  cand/score are [N][2][n_cand]; an entry is live if its
+// code is >= 0 and its BF16 score is within the row margin of the better of the two group maxima.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) rescore_kernel(const float* __restrict__ z, Lay L,
                                                      const float* __restrict__ E,
                                                      const float* __restrict__ e_sq, int K,
-                                                     const int32_t* __restrict__ cand, int n_cand,
+                                                     const int32_t* __restrict__ cand,
+                                                     const float* __restrict__ score,
+                                                     const float* __restrict__ row_margin, int n_cand,
                                                      const uint8_t* __restrict__ flags,
                                                      int64_t* __restrict__ idx,
                                                      int64_t* __restrict__ fb_rows,
@@ -169,22 +173,40 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const float* __restrict__ z
   extern __shared__ float tile[];
   __shared__ int need_tile;
   const int CP = L.C + 1;
+  const int nc2 = 2 * n_cand;
   const int64_t p0 = (int64_t)blockIdx.x * PT;
   const int np = (int)min((int64_t)PT, L.P - p0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = np * L.mult;
   const int64_t n0 = p0 * L.mult;
 
-  // Pass 0: rows with exactly one candidate are final; find out whether the tile needs z at all.
+  // Pass 0: rows with exactly one live candidate are final; find out whether the tile needs z at all.
   if (threadIdx.x == 0) need_tile = 0;
   __syncthreads();
   for (int r = threadIdx.x; r < rows; r += NT) {
     const int64_t n = n0 + r;
-    const int32_t c0 = cand[n * n_cand];
-    const bool multi = (n_cand > 1 && cand[n * n_cand + 1] >= 0) || c0 < 0;
-    if (multi) need_tile = 1;
-    else idx[n] = c0;
-    if (flags && (flags[n] & 1) && fb_rows) {
+    const int32_t* cr = cand + n * nc2;
+    const float* sr = score + n * nc2;
+    const float thr = fmaxf(sr[0], sr[n_cand]) - row_margin[n];   // slot 0 of each half = group maximum
+    int live = 0, only = -1;
+    for (int c = 0; c < nc2; ++c) {
+      const int k = cr[c];
+      if (k >= 0 && sr[c] >= thr) { ++live; only = k; }
+    }
+    if (live == 1) idx[n] = only;
+    else need_tile = 1;
+    // a half's list is incomplete w.r.t. the GLOBAL threshold if it was truncated (bit0) and its last
+    // slot is still live, or if it dropped entries (bit1) while its maximum is live
+    bool incomplete = false;
+    if (flags) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint8_t f = flags[2 * n + h];
+        incomplete |= (f & 1) && cr[h * n_cand + n_cand - 1] >= 0 && sr[h * n_cand + n_cand - 1] >= thr;
+        incomplete |= (f & 2) && sr[h * n_cand] >= thr;
+      }
+    }
+    if (incomplete && fb_rows) {
       int slot = atomicAdd(fb_count, 1);
       if (slot < fb_cap) {
         fb_rows[slot] = n;
@@ -199,8 +221,12 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const float* __restrict__ z
   __syncthreads();
   for (int r = warp; r < rows; r += NW) {
     const int64_t n = n0 + r;
-    const int32_t* cr = cand + n * n_cand;
-    if (!(n_cand > 1 && cr[1] >= 0) && cr[0] >= 0) continue;  // single candidate: done in pass 0
+    const int32_t* cr = cand + n * nc2;
+    const float* sr = score + n * nc2;
+    const float thr = fmaxf(sr[0], sr[n_cand]) - row_margin[n];
+    int live = 0;
+    for (int c = 0; c < nc2; ++c) live += (cr[c] >= 0 && sr[c] >= thr);
+    if (live == 1) continue;                              // done in pass 0
     const int p = r / L.mult, m = r - p * L.mult;
     const float* t = tile + p * CP + m * L.D;
     float zz = 0.f;
@@ -208,9 +234,9 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const float* __restrict__ z
     zz = warp_sum(zz);
     float best_d = INFINITY;
     int best_k = 0x7fffffff;
-    for (int c = 0; c < n_cand; ++c) {
+    for (int c = 0; c < nc2; ++c) {
       const int k = cr[c];
-      if (k < 0 || k >= K) continue;
+      if (k < 0 || k >= K || !(sr[c] >= thr)) continue;
       const float* e = E + (size_t)k * L.D;
       float dot = 0.f;
       for (int j = lane; j < L.D; j += 32) dot = fmaf(t[j], __ldg(e + j), dot);
@@ -524,19 +550,21 @@ extern "C" int ccvsq_pack_latents(const float* z, ccvsq_layout lay, void* z_bf16
 }
 
 extern "C" int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, const float* e_sq, int K,
-                             const int32_t* cand_idx, int n_cand, const uint8_t* flags, int64_t* idx,
-                             int64_t* fallback_rows, int32_t* fallback_count, int64_t fallback_capacity,
-                             void* stream) {
-  CCVSQ_REQUIRE(z && E && e_sq && cand_idx && idx, CCVSQ_NULL_POINTER, "rescore: null pointer");
+                             const int32_t* cand_idx, const float* cand_score, const float* row_margin,
+                             int n_cand, const uint8_t* flags, int64_t* idx, int64_t* fallback_ws,
+                             int32_t* fallback_count, int64_t fallback_capacity, void* stream) {
+  CCVSQ_REQUIRE(z && E && e_sq && cand_idx && cand_score && row_margin && idx, CCVSQ_NULL_POINTER,
+                "rescore: null pointer");
   CCVSQ_REQUIRE(n_cand >= 1 && n_cand <= CCVSQ_MAX_CAND, CCVSQ_BAD_SHAPE, "rescore: n_cand=%d", n_cand);
-  CCVSQ_REQUIRE((fallback_rows == nullptr) == (fallback_count == nullptr), CCVSQ_NULL_POINTER,
-                "rescore: fallback_rows and fallback_count must be given together");
+  CCVSQ_REQUIRE((fallback_ws == nullptr) == (fallback_count == nullptr), CCVSQ_NULL_POINTER,
+                "rescore: fallback_ws and fallback_count must be given together");
   Lay L;
   if (int rc = make_lay(lay, &L)) return rc;
   const size_t smem = tile_smem_bytes(L);
   if (int rc = enable_smem(rescore_kernel, smem)) return rc;
   rescore_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(
-      z, L, E, e_sq, K, cand_idx, n_cand, flags, idx, fallback_rows, fallback_count, fallback_capacity);
+      z, L, E, e_sq, K, cand_idx, cand_score, row_margin, n_cand, flags, idx, fallback_ws, fallback_count,
+      fallback_capacity);
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
 }

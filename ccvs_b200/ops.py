@@ -172,9 +172,26 @@ def search_exact(z: torch.Tensor, lay: Layout, cb: PreparedCodebook) -> torch.Te
 
 @dataclass
 class ScreenResult:
-    cand_idx: torch.Tensor    # [N, n_cand] int32, -1 padded
-    cand_score: torch.Tensor  # [N, n_cand] fp32
-    flags: torch.Tensor       # [N] uint8, bit0 = more than n_cand codes inside the margin
+    cand_idx: torch.Tensor    # [N, 2, n_cand] int32, -1 padded (two epilogue halves, see ccvsq.h)
+    cand_score: torch.Tensor  # [N, 2, n_cand] fp32, slot 0 of each half = that half's maximum
+    flags: torch.Tensor       # [N, 2] uint8, bit0 = more than n_cand codes inside the margin
+    margin: torch.Tensor      # [N_pad] fp32 row margins the screen used
+
+    def merged(self):
+        """(idx [N, 2*n_cand] int32 with -1 for dead entries, score, flag [N] bool) after applying
+        the global per-row threshold — what ccvsq_rescore sees (tests / diagnostics)."""
+        N = self.cand_idx.shape[0]
+        sc = self.cand_score.view(N, -1)
+        ci = self.cand_idx.view(N, -1)
+        thr = torch.maximum(self.cand_score[:, 0, 0], self.cand_score[:, 1, 0]) - self.margin[:N]
+        live = (ci >= 0) & (sc >= thr.unsqueeze(1))
+        nc = self.cand_idx.shape[2]
+        f = self.flags.view(N, 2)
+        last_live = live.view(N, 2, nc)[:, :, -1]
+        max_live = self.cand_score[:, :, 0] >= thr.unsqueeze(1)
+        incomplete = (((f & 1) != 0) & last_live) | (((f & 2) != 0) & max_live)
+        return torch.where(live, ci, torch.full_like(ci, -1)), torch.where(live, sc, torch.full_like(sc, float("-inf"))), \
+            incomplete.any(dim=1)
 
 
 def pack_latents(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, margin_tau: float) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -188,24 +205,24 @@ def pack_latents(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, margin_tau:
 
 def screen(zb: torch.Tensor, margin: torch.Tensor, cb: PreparedCodebook, N: int, n_cand: int = 4) -> ScreenResult:
     dev = zb.device
-    cand_idx = torch.empty(N, n_cand, dtype=torch.int32, device=dev)
-    cand_score = torch.empty(N, n_cand, dtype=torch.float32, device=dev)
-    flags = torch.empty(N, dtype=torch.uint8, device=dev)
+    cand_idx = torch.empty(N, 2, n_cand, dtype=torch.int32, device=dev)
+    cand_score = torch.empty(N, 2, n_cand, dtype=torch.float32, device=dev)
+    flags = torch.empty(N, 2, dtype=torch.uint8, device=dev)
     _call("ccvsq_screen", _ptr(zb), _ptr(margin), _ptr(cb.e_bf16), _ptr(cb.bias), N, cb.K, cb.D, n_cand,
-                        _ptr(cand_idx), _ptr(cand_score), _ptr(flags), _stream(dev))
-    return ScreenResult(cand_idx, cand_score, flags)
+          _ptr(cand_idx), _ptr(cand_score), _ptr(flags), _stream(dev))
+    return ScreenResult(cand_idx, cand_score, flags, margin)
 
 
 def screen_dump(zb: torch.Tensor, margin: torch.Tensor, cb: PreparedCodebook, N: int, n_cand: int = 4):
     """Diagnostic: screen + the full fp32 score matrix [N_pad, K_pad] (tests / debugging only)."""
     dev = zb.device
-    cand_idx = torch.empty(N, n_cand, dtype=torch.int32, device=dev)
-    cand_score = torch.empty(N, n_cand, dtype=torch.float32, device=dev)
-    flags = torch.empty(N, dtype=torch.uint8, device=dev)
+    cand_idx = torch.empty(N, 2, n_cand, dtype=torch.int32, device=dev)
+    cand_score = torch.empty(N, 2, n_cand, dtype=torch.float32, device=dev)
+    flags = torch.empty(N, 2, dtype=torch.uint8, device=dev)
     scores = torch.full((zb.shape[0], cb.e_bf16.shape[0]), float("nan"), dtype=torch.float32, device=dev)
     _call("ccvsq_screen_dump", _ptr(zb), _ptr(margin), _ptr(cb.e_bf16), _ptr(cb.bias), N, cb.K, cb.D, n_cand,
           _ptr(cand_idx), _ptr(cand_score), _ptr(flags), _ptr(scores), _stream(dev))
-    return ScreenResult(cand_idx, cand_score, flags), scores
+    return ScreenResult(cand_idx, cand_score, flags, margin), scores
 
 
 def rescore(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, sr: ScreenResult, exact_fallback: bool = True,
@@ -213,14 +230,15 @@ def rescore(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, sr: ScreenResult
     dev = z.device
     N = lay.rows
     idx = torch.empty(N, dtype=torch.int64, device=dev)
-    n_cand = sr.cand_idx.shape[1]
+    n_cand = sr.cand_idx.shape[2]
     fb_rows = fb_count = None
     cap = 0
     if exact_fallback:
         cap = min(N, fallback_capacity)
         fb_rows = torch.empty(2 * cap, dtype=torch.int64, device=dev)     # rows | packed keys
         fb_count = torch.zeros(2, dtype=torch.int32, device=dev)          # queued rows, scratch counter
-    _call("ccvsq_rescore", _ptr(z), lay, _ptr(cb.weight), _ptr(cb.e_sq), cb.K, _ptr(sr.cand_idx), n_cand,
+    _call("ccvsq_rescore", _ptr(z), lay, _ptr(cb.weight), _ptr(cb.e_sq), cb.K, _ptr(sr.cand_idx),
+          _ptr(sr.cand_score), _ptr(sr.margin), n_cand,
                          _ptr(sr.flags), _ptr(idx), _ptr(fb_rows), _ptr(fb_count), cap, _stream(dev))
     if exact_fallback:
         # rows with more codes inside the margin than candidate slots: exact FP32 search, count read

@@ -90,12 +90,18 @@ int ccvsq_pack_latents(const float* z, ccvsq_layout lay, void* z_bf16, float* ro
                        float margin_scale, const float* e_max, void* stream);
 
 /* ccvsq_screen: s[n,k] = <bf16(z_n), bf16(e_k)> - 0.5||e_k||^2 on tcgen05 tensor cores with a
- * fused running candidate selection per row.  Output per row: up to n_cand candidates sorted by
- * (score desc, index asc), -1 padded; only codes whose score is within row_margin[n] of the row
- * maximum are kept.  flags[n] bit0 = more than n_cand codes were within the margin (the caller
- * should fall back to ccvsq_search_exact_rows for that row).
- * Requires D % 64 == 0, 64 <= D <= 512; K_pad % 256 == 0; N_pad % 128 == 0.
- *   cand_idx [N, n_cand] int32 out; cand_score [N, n_cand] fp32 out; flags [N] uint8 out.    */
+ * fused running candidate selection per row.  The kernel's two epilogue groups each own half of
+ * the code tiles (even / odd tiles of 256 codes) and report independently, so every per-row output
+ * has two halves h = 0, 1:
+ *   cand_idx   [N, 2, n_cand] int32: codes whose score is within row_margin[n] of that half's
+ *                                    maximum, sorted by (score desc, code asc), -1 padded
+ *   cand_score [N, 2, n_cand] fp32 : their BF16-path scores (-inf padded); slot 0 = half maximum
+ *   flags      [N, 2] uint8        : bit0 = more than n_cand codes were inside that half's margin
+ *                                    (list truncated), bit1 = the half's internal list overflowed
+ *                                    and dropped a code that may be inside the margin
+ * ccvsq_rescore merges the halves.
+ * Requires D % 64 == 0, 64 <= D <= 512.  z_bf16 is [N_pad, D] (N_pad = N rounded up to 128), E_bf16
+ * [K_pad, D] and bias [K_pad] (K_pad = K rounded up to 256), row_margin [N_pad].               */
 int ccvsq_screen(const void* z_bf16, const float* row_margin, const void* E_bf16, const float* bias,
                  int64_t N, int K, int D, int n_cand, int32_t* cand_idx, float* cand_score,
                  uint8_t* flags, void* stream);
@@ -106,16 +112,20 @@ int ccvsq_screen_dump(const void* z_bf16, const float* row_margin, const void* E
                       const float* bias, int64_t N, int K, int D, int n_cand, int32_t* cand_idx,
                       float* cand_score, uint8_t* flags, float* scores, void* stream);
 
-/* ccvsq_rescore: FP32 re-evaluation of the screened candidates with the reference's formula and
- * lowest-index tie-break (quantize.py:45-50); rows with a single candidate take it directly.
- * Rows whose flags bit0 is set are queued for the exact fallback:
+/* ccvsq_rescore: merges the two halves of the screen output (a candidate is live if its score is
+ * within row_margin[n] of the better half maximum), then re-evaluates the live candidates in FP32
+ * with the reference's formula and lowest-index tie-break (quantize.py:45-50); rows with a single
+ * live candidate take it directly without touching z.
+ * Rows whose candidate set is incomplete w.r.t. the merged threshold (a truncated half whose last
+ * slot is still live, or a half that dropped entries while its maximum is live) are queued for the
+ * exact fallback:
  *   fallback_ws    int64 [2*fallback_capacity]: row numbers, then packed (distance, code) keys
  *   fallback_count int32 [2], zeroed by the caller: [0] rows queued, [1] scratch counter
  * (both may be NULL to ignore overflow rows).                                                   */
 int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, const float* e_sq, int K,
-                  const int32_t* cand_idx, int n_cand, const uint8_t* flags, int64_t* idx,
-                  int64_t* fallback_ws, int32_t* fallback_count, int64_t fallback_capacity,
-                  void* stream);
+                  const int32_t* cand_idx, const float* cand_score, const float* row_margin,
+                  int n_cand, const uint8_t* flags, int64_t* idx, int64_t* fallback_ws,
+                  int32_t* fallback_count, int64_t fallback_capacity, void* stream);
 
 /* Exact FP32 search restricted to the rows queued by ccvsq_rescore (count read on the device, no
  * host sync).  The codebook is split across CTAs, partial minima meet through 64-bit atomicMin on

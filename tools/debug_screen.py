@@ -45,9 +45,11 @@ def run(N, K, D, seed=0):
         print("  got[1,:8]", got[1, :8].cpu().tolist())
         print("  ref[1,:8]", ref[1, :8].cpu().tolist())
     top = ref[:N, :K].max(dim=1)
-    ok = (sr.cand_idx[:, 0].long() == top.indices)
+    ci, sc, flag = sr.merged()
+    best = ci.gather(1, sc.argmax(1, keepdim=True)).squeeze(1).long()
+    ok = (best == top.indices)
     print(f"  top-1 candidate == torch argmax on {float(ok.float().mean()) * 100:.3f}% of rows; "
-          f"flags set on {int(sr.flags.sum())} rows; mean #cands {float((sr.cand_idx >= 0).sum(1).float().mean()):.2f}")
+          f"flags set on {int(flag.sum())} rows; mean #cands {float((ci >= 0).sum(1).float().mean()):.2f}")
     return float(err[~nan].max()) if (~nan).any() else float("inf")
 
 

@@ -13,9 +13,9 @@ for wl in sys.argv[1:] or ["c2", "c3"]:
     zb, margin = ops.pack_latents(z, lay, pcb, 1.0)
     sr = ops.screen(zb, margin, pcb, lay.rows, 4)
     torch.cuda.synchronize()
-    nc = (sr.cand_idx >= 0).sum(1)
-    print(wl, "rows", n, "flags", int(sr.flags.sum()), "ncand hist", torch.bincount(nc, minlength=5).tolist(),
-          "margin mean", float(margin[:n].mean()), "gap top1-top2 min", float((sr.cand_score[:, 0] - sr.cand_score[:, 1]).min()))
-    fl = sr.flags.nonzero().view(-1)[:5]
-    for r in fl.tolist():
+    ci, sc, flag = sr.merged()
+    nc = (ci >= 0).sum(1)
+    print(wl, "rows", n, "flags", int(flag.sum()), "ncand hist", torch.bincount(nc, minlength=5).tolist(),
+          "margin mean", float(margin[:n].mean()))
+    for r in flag.nonzero().view(-1)[:5].tolist():
         print("  row", r, sr.cand_idx[r].tolist(), sr.cand_score[r].tolist(), float(margin[r]))
