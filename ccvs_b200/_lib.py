@@ -50,6 +50,7 @@ SIGNATURES = {
     "ccvsq_pack_latents": (c_int, [_P, Layout, _P, _P, c_float, _P, _P]),
     "ccvsq_screen": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ccvsq_screen_dump": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "ccvsq_screen_trace": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "ccvsq_rescore": (c_int, [_P, Layout, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, c_int64, _P]),
     "ccvsq_search_exact_rows": (c_int, [_P, Layout, _P, _P, c_int, _P, _P, c_int64, _P, _P]),
     "ccvsq_assign": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, _P, _P]),

@@ -156,7 +156,7 @@ __host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int BN, int n
   s.b = off;    off += (uint32_t)nst * BN * BK * 2;
   s.ring = off; off += 2u * LIST_BYTES;             // [group]{ [slot][row] float4 | [slot][row] u32 }
   s.bias = off; off += 2u * 2u * BN * 4;            // [group][parity][BN]
-  s.bars = off; off += 256;
+  s.bars = off; off += 512;
   s.total = off;
   return s;
 }
@@ -195,26 +195,37 @@ __device__ __noinline__ void list_compact(uint32_t sc_base, uint32_t co_base, ui
     }
     dropped_max = fmaxf(dropped_max, lo);
     --w;
-    if (lo_e != w) {                  // move the last entry into the hole
+    for (uint32_t e = lo_e; e < w; ++e) {   // close the hole, keeping entries in increasing code order
       float a, b, c, d;
       uint32_t code;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(sc_base + w * SC_STRIDE));
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + w * CO_STRIDE));
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sc_base + lo_e * SC_STRIDE), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(co_base + lo_e * CO_STRIDE), "r"(code) : "memory");
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(sc_base + (e + 1) * SC_STRIDE));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + (e + 1) * CO_STRIDE));
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sc_base + e * SC_STRIDE), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(co_base + e * CO_STRIDE), "r"(code) : "memory");
     }
   }
   psc = sc_base + w * SC_STRIDE;
   pco = co_base + w * CO_STRIDE;
 }
 
-template <int BN, int NST>
+// TRACE: diagnostic instantiation (ccvsq_screen_trace) — CTA 0 records (clock64, event) pairs per role.
+#define CCVSQ_TRACE_EVENT(role, code)                                                            \
+  do {                                                                                           \
+    if (TRACE && blockIdx.x == 0 && trace_n[role] < 4000) {                                      \
+      trace[(role) * 4000 + trace_n[role]] = (clock64() << 8) | (long long)(code);               \
+      ++trace_n[role];                                                                           \
+    }                                                                                            \
+  } while (0)
+
+template <int BN, int NST, bool TRACE>
 __global__ void __launch_bounds__(SCREEN_THREADS, 1)
 screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               const float* __restrict__ bias, const float* __restrict__ row_margin, int64_t N,
               int num_row_tiles, int K, int K_pad, int dblk, int n_cand,
               int32_t* __restrict__ cand_idx, float* __restrict__ cand_score,
-              uint8_t* __restrict__ flags, float* __restrict__ dbg_scores) {
+              uint8_t* __restrict__ flags, float* __restrict__ dbg_scores, long long* __restrict__ trace) {
+  int trace_n[4] = {0, 0, 0, 0};
+  (void)trace_n;
   extern __shared__ __align__(1024) uint8_t smem[];
   const ScreenSmem lay = screen_smem_layout(dblk, BN, NST);
   const uint32_t smem_base = smem_u32(smem);
@@ -227,12 +238,14 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   const uint32_t bar0 = smem_base + lay.bars;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (NST + s); };
-  const uint32_t a_full = bar0 + 8u * (2 * NST);
-  const uint32_t a_empty = bar0 + 8u * (2 * NST + 1);
-  auto tmem_full = [&](int b) { return bar0 + 8u * (2 * NST + 2 + b); };
-  auto tmem_empty = [&](int b) { return bar0 + 8u * (2 * NST + 4 + b); };
-  auto bias_rdy = [&](int g) { return bar0 + 8u * (2 * NST + 6 + g); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + lay.bars + 8u * (2 * NST + 8));
+  auto tmem_full = [&](int b) { return bar0 + 8u * (2 * NST + b); };
+  auto tmem_empty = [&](int b) { return bar0 + 8u * (2 * NST + 2 + b); };
+  auto bias_rdy = [&](int g) { return bar0 + 8u * (2 * NST + 4 + g); };
+  // the stationary A tile is handed over per 64-dim block, so the next row tile's blocks stream in
+  // while the last code tile of the current row tile is still being multiplied
+  auto a_full = [&](int kb) { return bar0 + 8u * (2 * NST + 6 + kb); };
+  auto a_empty = [&](int kb) { return bar0 + 8u * (2 * NST + 14 + kb); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + lay.bars + 8u * (2 * NST + 22));
 
   if ((smem_base & 1023u) != 0) __trap();   // SWIZZLE_128B needs 1024-byte aligned tiles
 
@@ -242,8 +255,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
+    for (int kb = 0; kb < 8; ++kb) { mbar_init(a_full(kb), 1); mbar_init(a_empty(kb), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full(b), 1);
       mbar_init(tmem_empty(b), 128);
@@ -267,20 +279,22 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       for (int tile = blockIdx.x; tile < num_row_tiles; tile += gridDim.x) {
-        mbar_wait(a_empty, a_phase ^ 1);
-        mbar_arrive_expect_tx(a_full, (uint32_t)dblk * A_BLOCK_BYTES);
-        for (int kb = 0; kb < dblk; ++kb)
-          tma_load_2d(smem_base + lay.a + kb * A_BLOCK_BYTES, &map_a, a_full, kb * BK, tile * BM);
-        a_phase ^= 1;
         for (int j = 0; j < num_n_tiles; ++j) {
           for (int kb = 0; kb < dblk; ++kb) {
+            if (j == 0) {   // A block kb of this row tile, as soon as the previous tile's MMAs released it
+              mbar_wait(a_empty(kb), a_phase ^ 1);
+              mbar_arrive_expect_tx(a_full(kb), A_BLOCK_BYTES);
+              tma_load_2d(smem_base + lay.a + kb * A_BLOCK_BYTES, &map_a, a_full(kb), kb * BK, tile * BM);
+            }
             mbar_wait(empty_bar(stage), phase ^ 1);
+            CCVSQ_TRACE_EVENT(0, 1);                       // B stage issued
             mbar_arrive_expect_tx(full_bar(stage), B_STAGE_BYTES);
             tma_load_2d(smem_base + lay.b + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK,
                         j * BN);
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
         }
+        a_phase ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -291,17 +305,18 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       uint32_t phase = 0, a_phase = 0;
       uint32_t uses[2] = {0, 0};
       for (int tile = blockIdx.x; tile < num_row_tiles; tile += gridDim.x) {
-        mbar_wait(a_full, a_phase);
-        a_phase ^= 1;
-        tc_fence_after();
         for (int j = 0; j < num_n_tiles; ++j) {
           const int b = j & 1;
+          CCVSQ_TRACE_EVENT(1, 1);                         // start waiting for the accumulator buffer
           mbar_wait(tmem_empty(b), (uses[b] & 1) ^ 1);
+          CCVSQ_TRACE_EVENT(1, 2);                         // accumulator buffer free
           ++uses[b];
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
           for (int kb = 0; kb < dblk; ++kb) {
+            if (j == 0) mbar_wait(a_full(kb), a_phase);
             mbar_wait(full_bar(stage), phase);
+            CCVSQ_TRACE_EVENT(1, 3);                       // operands of this k-block landed
             tc_fence_after();
             const uint32_t a_addr = smem_base + lay.a + kb * A_BLOCK_BYTES;
             const uint32_t b_addr = smem_base + lay.b + stage * B_STAGE_BYTES;
@@ -312,11 +327,13 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
               umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(empty_bar(stage));      // smem stage reusable once these MMAs retire
+            if (j == num_n_tiles - 1) umma_commit(a_empty(kb));   // last reader of A block kb
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
           umma_commit(tmem_full(b));            // accumulator tile j complete
+          CCVSQ_TRACE_EVENT(1, 4);                         // tile issued
         }
-        umma_commit(a_empty);                   // A tile no longer read
+        a_phase ^= 1;
       }
     }
   } else if (warp >= 4) {
@@ -363,10 +380,12 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             for (int u = 0; u < BN / 128; ++u) nb[u] = __ldg(bias + (size_t)jn * BN + u * 128 + tg);
           }
         }
+        if (tg == 0) CCVSQ_TRACE_EVENT(2 + g, 1);          // waiting for accumulator tile
         mbar_wait(tmem_full(g), full_phase);
         full_phase ^= 1;
         tc_fence_after();
-        mbar_wait(bias_rdy(g), it & 1);         // all 128 threads of the group stored their bias slice
+        mbar_wait(bias_rdy(g), it & 1);
+        if (tg == 0) CCVSQ_TRACE_EVENT(2 + g, 2);          // tile available         // all 128 threads of the group stored their bias slice
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
         const int col0 = j * BN;
 
@@ -436,41 +455,45 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         }
         tc_fence_before();
         mbar_arrive(tmem_empty(g));
+        if (tg == 0) CCVSQ_TRACE_EVENT(2 + g, 3);          // tile consumed
       }
 
       // ---- this group's candidates for the row: every listed code with score >= runmax - margin,
-      //      sorted by (score desc, code asc), at most n_cand of them
+      //      sorted by (score desc, code asc), at most n_cand of them.  The list is in increasing
+      //      code order, so a strict '>' scan keeps the lowest code among equal scores.
       if (row < N) {
         const int64_t obase = (row * 2 + g) * n_cand;
         const float thr = runmax - margin;
         const uint32_t n = (pco - co_base) / CO_STRIDE;
         uint32_t within = 0;
         float best_s = -INFINITY;
-        int best_i = 0x7fffffff;
+        int best_i = -1;
         for (uint32_t e = 0; e < n; ++e) {
           float sc[4];
           uint32_t code;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = (int)code + u;
-            if (sc[u] >= thr && i < K) {
-              ++within;
-              if (sc[u] > best_s || (sc[u] == best_s && i < best_i)) { best_s = sc[u]; best_i = i; }
-            }
+          for (int u = 0; u < 4; ++u) {      // branch-free (padding codes carry -inf and never pass)
+            within += (sc[u] >= thr) ? 1u : 0u;
+            const bool better = sc[u] > best_s;
+            best_s = better ? sc[u] : best_s;
+            best_i = better ? (int)code + u : best_i;
           }
         }
-        int written = 0;
-        if (within >= 1) {
-          cand_idx[obase] = best_i;
-          cand_score[obase] = best_s;
-          written = 1;
-        }
-        if (within > 1) {          // rare: near-ties; repeated selection in (score desc, code asc) order
+        if (within <= 1 && n_cand == 4) {   // the overwhelmingly common case: two 16-byte stores
+          *reinterpret_cast<int4*>(cand_idx + obase) = make_int4(within ? best_i : -1, -1, -1, -1);
+          *reinterpret_cast<float4*>(cand_score + obase) = make_float4(best_s, -INFINITY, -INFINITY, -INFINITY);
+        } else {
+          int written = 0;
+          if (within >= 1) {
+            cand_idx[obase] = best_i;
+            cand_score[obase] = best_s;
+            written = 1;
+          }
           float prev_s = best_s;
           int prev_i = best_i;
-          for (int c = 1; c < n_cand; ++c) {
+          for (int c = 1; c < n_cand && within > 1; ++c) {   // near-ties: repeated selection
             float bs_ = -INFINITY;
             int bi = 0x7fffffff;
             for (uint32_t e = 0; e < n; ++e) {
@@ -482,10 +505,9 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
               for (int u = 0; u < 4; ++u) {
                 const int i = (int)code + u;
                 const float x = sc[u];
-                if (!(x >= thr) || i >= K) continue;
                 const bool after_prev = (x < prev_s) || (x == prev_s && i > prev_i);
                 const bool better = (x > bs_) || (x == bs_ && i < bi);
-                if (after_prev && better) { bs_ = x; bi = i; }
+                if (x >= thr && after_prev && better) { bs_ = x; bi = i; }
               }
             }
             if (bi == 0x7fffffff) break;
@@ -495,11 +517,12 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             prev_i = bi;
             ++written;
           }
+          for (int c = written; c < n_cand; ++c) {
+            cand_idx[obase + c] = -1;
+            cand_score[obase + c] = -INFINITY;
+          }
         }
-        for (int c = written; c < n_cand; ++c) {
-          cand_idx[obase + c] = -1;
-          cand_score[obase + c] = -INFINITY;
-        }
+        if (tg == 0) CCVSQ_TRACE_EVENT(2 + g, 4);          // row tile finalised
         flags[row * 2 + g] = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped_max >= thr ? 2 : 0));
       }
     }
@@ -551,19 +574,19 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int64
   return CCVSQ_OK;
 }
 
-template <int BN, int NST>
+template <int BN, int NST, bool TRACE = false>
 static int launch_screen(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias,
                          const float* row_margin, int64_t N, int tiles, int K, int K_pad, int dblk,
                          int n_cand, int32_t* cand_idx, float* cand_score, uint8_t* flags,
-                         float* dbg_scores, cudaStream_t st) {
+                         float* dbg_scores, cudaStream_t st, long long* trace = nullptr) {
   const ScreenSmem lay = screen_smem_layout(dblk, BN, NST);
   const size_t smem = lay.total;
   CCVSQ_REQUIRE(smem <= 227 * 1024, CCVSQ_UNSUPPORTED, "screen: %zu bytes of shared memory needed", smem);
-  auto kern = screen_kernel<BN, NST>;
+  auto kern = screen_kernel<BN, NST, TRACE>;
   if (int rc = enable_smem(kern, smem)) return rc;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   kern<<<grid, SCREEN_THREADS, smem, st>>>(ma, mb, bias, row_margin, N, tiles, K, K_pad, dblk, n_cand,
-                                         cand_idx, cand_score, flags, dbg_scores);
+                                         cand_idx, cand_score, flags, dbg_scores, trace);
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
 }
@@ -574,15 +597,15 @@ using namespace ccvsq;
 
 static int screen_impl(const void* z_bf16, const float* row_margin, const void* E_bf16, const float* bias,
                        int64_t N, int K, int D, int n_cand, int32_t* cand_idx, float* cand_score,
-                       uint8_t* flags, float* dbg_scores, void* stream) {
+                       uint8_t* flags, float* dbg_scores, void* stream, long long* trace = nullptr) {
   CCVSQ_REQUIRE(z_bf16 && row_margin && E_bf16 && bias && cand_idx && cand_score && flags,
                 CCVSQ_NULL_POINTER, "screen: null pointer");
   CCVSQ_REQUIRE(N > 0 && K > 0, CCVSQ_BAD_SHAPE, "screen: N=%lld K=%d", (long long)N, K);
   CCVSQ_REQUIRE(D % 64 == 0 && D >= 64 && D <= 512, CCVSQ_UNSUPPORTED,
                 "screen: D=%d unsupported by the tensor-core path (need 64 <= D <= 512, D %% 64 == 0)", D);
   CCVSQ_REQUIRE(n_cand >= 1 && n_cand <= CCVSQ_MAX_CAND, CCVSQ_BAD_SHAPE, "screen: n_cand=%d", n_cand);
-  CCVSQ_REQUIRE((((uintptr_t)z_bf16 | (uintptr_t)E_bf16) & 15) == 0, CCVSQ_MISALIGNED,
-                "screen: BF16 operands must be 16-byte aligned");
+  CCVSQ_REQUIRE((((uintptr_t)z_bf16 | (uintptr_t)E_bf16 | (uintptr_t)cand_idx | (uintptr_t)cand_score) & 15) == 0,
+                CCVSQ_MISALIGNED, "screen: BF16 operands and candidate arrays must be 16-byte aligned");
   const int64_t N_pad = ((N + BM - 1) / BM) * BM;
   const int K_pad = ((K + 255) / 256) * 256;
   const int64_t tiles64 = N_pad / BM;
@@ -596,6 +619,9 @@ static int screen_impl(const void* z_bf16, const float* row_margin, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   if (dblk <= 4) {
     if (int rc = make_map(enc, &mb, E_bf16, K_pad, D, 256)) return rc;
+    if (trace)
+      return launch_screen<256, 4, true>(ma, mb, bias, row_margin, N, (int)tiles64, K, K_pad, dblk, n_cand,
+                                         cand_idx, cand_score, flags, dbg_scores, st, trace);
     return launch_screen<256, 4>(ma, mb, bias, row_margin, N, (int)tiles64, K, K_pad, dblk, n_cand,
                                  cand_idx, cand_score, flags, dbg_scores, st);
   }
@@ -617,4 +643,15 @@ extern "C" int ccvsq_screen_dump(const void* z_bf16, const float* row_margin, co
   CCVSQ_REQUIRE(scores, CCVSQ_NULL_POINTER, "screen_dump: scores must be non-null");
   return screen_impl(z_bf16, row_margin, E_bf16, bias, N, K, D, n_cand, cand_idx, cand_score, flags, scores,
                      stream);
+}
+
+// Diagnostic: CTA 0 records a per-role event timeline, trace is int64 [4][4000] zero-filled by the
+// caller (roles: 0 TMA producer, 1 MMA issuer, 2/3 epilogue groups; value = clock64 << 8 | event).
+extern "C" int ccvsq_screen_trace(const void* z_bf16, const float* row_margin, const void* E_bf16,
+                                  const float* bias, int64_t N, int K, int D, int n_cand, int32_t* cand_idx,
+                                  float* cand_score, uint8_t* flags, long long* trace, void* stream) {
+  CCVSQ_REQUIRE(trace, CCVSQ_NULL_POINTER, "screen_trace: trace must be non-null");
+  CCVSQ_REQUIRE(D <= 256, CCVSQ_UNSUPPORTED, "screen_trace: only the BN=256 configuration is traced");
+  return screen_impl(z_bf16, row_margin, E_bf16, bias, N, K, D, n_cand, cand_idx, cand_score, flags, nullptr,
+                     stream, trace);
 }

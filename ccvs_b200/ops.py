@@ -21,7 +21,7 @@ _L = _lib.load()  # fail loudly at import time if the extension is missing
 # kernels enqueued by each entry point (ccvsq_prepare_codebook: + one 4-byte memset node)
 _KERNELS_PER_CALL = {
     "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_pack_latents": 1, "ccvsq_screen": 1,
-    "ccvsq_screen_dump": 1, "ccvsq_rescore": 1, "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1,
+    "ccvsq_screen_dump": 1, "ccvsq_screen_trace": 1, "ccvsq_rescore": 1, "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1,
     "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1, "ccvsq_finalize": 1, "ccvsq_ema_update": 2,
 }
 
@@ -223,6 +223,18 @@ def screen_dump(zb: torch.Tensor, margin: torch.Tensor, cb: PreparedCodebook, N:
     _call("ccvsq_screen_dump", _ptr(zb), _ptr(margin), _ptr(cb.e_bf16), _ptr(cb.bias), N, cb.K, cb.D, n_cand,
           _ptr(cand_idx), _ptr(cand_score), _ptr(flags), _ptr(scores), _stream(dev))
     return ScreenResult(cand_idx, cand_score, flags, margin), scores
+
+
+def screen_trace(zb: torch.Tensor, margin: torch.Tensor, cb: PreparedCodebook, N: int, n_cand: int = 4):
+    """Diagnostic: per-role event timeline of CTA 0, int64 [4, 4000] (clock64 << 8 | event)."""
+    dev = zb.device
+    cand_idx = torch.empty(N, 2, n_cand, dtype=torch.int32, device=dev)
+    cand_score = torch.empty(N, 2, n_cand, dtype=torch.float32, device=dev)
+    flags = torch.empty(N, 2, dtype=torch.uint8, device=dev)
+    trace = torch.zeros(4, 4000, dtype=torch.int64, device=dev)
+    _call("ccvsq_screen_trace", _ptr(zb), _ptr(margin), _ptr(cb.e_bf16), _ptr(cb.bias), N, cb.K, cb.D, n_cand,
+          _ptr(cand_idx), _ptr(cand_score), _ptr(flags), _ptr(trace), _stream(dev))
+    return trace
 
 
 def rescore(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, sr: ScreenResult, exact_fallback: bool = True,

@@ -112,6 +112,12 @@ int ccvsq_screen_dump(const void* z_bf16, const float* row_margin, const void* E
                       const float* bias, int64_t N, int K, int D, int n_cand, int32_t* cand_idx,
                       float* cand_score, uint8_t* flags, float* scores, void* stream);
 
+/* Diagnostic variant: CTA 0 records a per-role event timeline into trace (int64 [4][4000], zeroed
+ * by the caller; value = clock64 << 8 | event code).  Performance debugging only.               */
+int ccvsq_screen_trace(const void* z_bf16, const float* row_margin, const void* E_bf16,
+                       const float* bias, int64_t N, int K, int D, int n_cand, int32_t* cand_idx,
+                       float* cand_score, uint8_t* flags, long long* trace, void* stream);
+
 /* ccvsq_rescore: merges the two halves of the screen output (a candidate is live if its score is
  * within row_margin[n] of the better half maximum), then re-evaluates the live candidates in FP32
  * with the reference's formula and lowest-index tie-break (quantize.py:45-50); rows with a single
