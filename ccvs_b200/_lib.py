@@ -45,13 +45,13 @@ _P = c_void_p
 SIGNATURES = {
     "ccvsq_version": (c_int, []),
     "ccvsq_last_error": (c_char_p, []),
-    "ccvsq_prepare_codebook": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
+    "ccvsq_codebook_rows": (c_int, [c_int]),
+    "ccvsq_prepare_codebook": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
     "ccvsq_search_exact": (c_int, [_P, Layout, _P, _P, c_int, _P, _P]),
-    "ccvsq_pack_latents": (c_int, [_P, Layout, _P, _P, c_float, _P, _P]),
-    "ccvsq_screen": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
-    "ccvsq_screen_dump": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
-    "ccvsq_screen_trace": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
-    "ccvsq_rescore": (c_int, [_P, Layout, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, c_int64, _P]),
+    "ccvsq_screen": (c_int, [_P, Layout, _P, _P, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P]),
+    "ccvsq_screen_debug": (c_int, [_P, Layout, _P, _P, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                   _P, _P]),
+    "ccvsq_rescore": (c_int, [_P, Layout, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "ccvsq_search_exact_rows": (c_int, [_P, Layout, _P, _P, c_int, _P, _P, c_int64, _P, _P]),
     "ccvsq_assign": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, _P, _P]),
     "ccvsq_gather": (c_int, [_P, _P, c_int, Layout, _P, _P, _P]),

@@ -91,6 +91,11 @@ inline int enable_smem(Kern kern, size_t bytes) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// tensor-core screen: codes per accumulator tile, and the K-extension that carries the bias
+// (the BF16 codebook shadow is [ccvsq_codebook_rows(K), D + SCREEN_EXT])
+constexpr int SCREEN_BN = 96;
+constexpr int SCREEN_EXT = 16;
+
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace ccvsq

@@ -4,21 +4,31 @@
 // pairs in FP32 and takes the row argmin.  argmin_k d[n,k] == argmax_k s[n,k] with
 //     s[n,k] = z_n.e_k - 0.5*||e_k||^2                     (||z_n||^2 is constant per row)
 // This kernel evaluates s on the 5th-gen tensor cores with BF16 operands / FP32 accumulation and
-// keeps, per row, every code whose score is within `row_margin[n]` of the row maximum (the margin
-// bounds the BF16 rounding noise).  The survivors are re-scored in FP32 by ccvsq_rescore, so the
-// final index equals the FP32 argmin whenever the FP32 winner is inside the margin.
+// keeps, per row, every code whose score is within a margin of the row maximum (the margin bounds
+// the BF16 rounding noise).  Rows with a single survivor are final; the others are queued for FP32
+// re-scoring (ccvsq_rescore), so the result equals the FP32 argmin whenever the FP32 winner is
+// inside the margin.
 //
-// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
-//   warp 0      TMA producer: A tile (128 latents x D, BF16, stationary for the whole code sweep)
-//               and a NST-deep ring of B stages (BN codes x 64 dims), 128B-swizzled, mbarrier-signalled
-//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16; accumulators
-//               double-buffered in TMEM (2 x BN columns) so the epilogue of code tile j overlaps the
-//               MMAs of tile j+1
+// Design (one persistent CTA per SM, CTAs paired into 2-CTA clusters, 512 threads, warp-specialised):
+//   * A operand (128 latent rows per CTA) lives in TENSOR MEMORY for the whole code sweep.  Loader
+//     warps read the FP32 latents straight from the caller's tensor (any ccvsq_layout: the
+//     NCHW->rows transpose of quantize.py:40-42 is pure addressing), round to BF16 and write the
+//     packed pairs with tcgen05.st.  No packing pass, no BF16 copy of z in HBM, no A traffic in
+//     shared memory.  Two A buffers (D <= 256) let the next row tile stream in under the MMAs.
+//   * B operand: BN=96 codes x (D+16) dims per tile, TMA-loaded (128B swizzle) into a ring of
+//     whole-tile slots.  With tcgen05.mma.cta_group::2 each CTA of the pair holds half the codes of
+//     a tile, so L2->SM and shared-memory traffic per FLOP are half those of a single-CTA MMA.
+//   * The bias -0.5||e||^2 is folded into the GEMM: the codebook shadow carries 16 extra columns
+//     (a 3-term BF16 split hi+mid+lo of the bias, exact to FP32), matched by a constant A block
+//     (1,1,1,0,...) in tensor memory.  The accumulator IS the score: the epilogue has no bias loads
+//     or adds, only max trees.
+//   * Accumulators (128 x 96 FP32) double-buffered in tensor memory; one epilogue warp per TMEM
+//     lane quadrant, one latent row per thread over ALL codes -> one candidate list per row.
+//   warp 0      TMA producer (both CTAs, each loads its half of every B tile)
+//   warp 1      MMA issuer (leader CTA of the pair only)
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue group 0 (even code tiles): tcgen05.ld 32 columns at a time, one latent row
-//   warps 8-11  epilogue group 1 (odd code tiles)   per thread, bias add, running max, candidate ring
-// After the last code tile of a row tile the two groups' candidate rings are merged, filtered by
-// (row max - margin), sorted by (score desc, index asc) and written out.
+//   warps 4-7   epilogue: tcgen05.ld 32 columns at a time, max tree, candidate list, outputs
+//   warps 8-15  A loaders: global FP32 -> BF16 -> tcgen05.st, row norms for the margin
 #include <cuda.h>
 #include <float.h>
 #include "common.cuh"
@@ -31,11 +41,29 @@ namespace ccvsq {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier given by a shared::cluster address (own or peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
@@ -54,12 +82,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.  The
+// clock is consulted only every 256 failed polls so the spin costs few issue slots.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+    if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();   // ~2 s
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {
@@ -71,31 +101,73 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
-                                            int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
-      "[%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+// 2-D tiled TMA load into this CTA's shared memory; `bar` is a shared::cluster barrier address (for
+// CG == 2 the leader CTA's barrier collects the bytes of both halves).
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T, BF16 x BF16 -> FP32
+template <int CG>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// Arrive on `bar` (same offset in every CTA of the group) once all previously issued MMAs retire.
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(mask)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -113,8 +185,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 format, version 1):
@@ -122,10 +208,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address  [0,14)
-  d |= (uint64_t)0 << 16;                            // LBO            [16,30)
   d |= (uint64_t)(1024 >> 4) << 32;                  // SBO            [32,46)
   d |= (uint64_t)1 << 46;                            // version = 1    [46,48)
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B   [61,64)
+  return d;
+}
+// K-major, no swizzle: 8-row x 16-byte core matrices; SBO = 128 B between 8-row groups, LBO = byte
+// distance between the two 16-byte K chunks of one 16-element K step.
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // LBO            [16,30)
+  d |= (uint64_t)(128 >> 4) << 32;                   // SBO
+  d |= (uint64_t)1 << 46;
   return d;
 }
 // kind::f16 instruction descriptor: FP32 accum, BF16 x BF16, both K-major, M x N.
@@ -136,27 +231,40 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // ------------------------------------------------------------------------------------------------
 // kernel configuration
 // ------------------------------------------------------------------------------------------------
-constexpr int BM = 128;            // latent rows per CTA tile (UMMA M)
-constexpr int BK = 64;             // dims per smem block (128 bytes of BF16 = one swizzle atom row)
-constexpr int LCAP = 6;                 // candidate-list entries per (row, epilogue group)
-constexpr uint32_t SC_STRIDE = 128 * 16;   // entry e of a row: 4 raw scores at sc_base + e*SC_STRIDE ...
-constexpr uint32_t CO_STRIDE = 128 * 4;    // ... and the first code of the group at co_base + e*CO_STRIDE
-constexpr uint32_t LIST_BYTES = LCAP * (SC_STRIDE + CO_STRIDE);   // per epilogue group
-constexpr int SCREEN_THREADS = 384;
-constexpr int A_BLOCK_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int BM = 128;              // latent rows per CTA (TMEM lanes)
+constexpr int BN = SCREEN_BN;        // codes per accumulator tile (UMMA N)
+constexpr int LCAP = 8;              // candidate-list entries (groups of 4 codes) per row
+constexpr uint32_t SC_STRIDE = BM * 16;   // entry e of a row: 4 raw scores at sc_base + e*SC_STRIDE ...
+constexpr uint32_t CO_STRIDE = BM * 4;    // ... and the first code of the group at co_base + e*CO_STRIDE
+constexpr uint32_t LIST_BYTES = LCAP * (SC_STRIDE + CO_STRIDE);
+constexpr int SCREEN_THREADS = 512;
+constexpr int MAX_SLOTS = 8;
+// tensor-memory columns (32-bit): two accumulators, the constant bias-extension A block, A buffers
+constexpr uint32_t TM_ACC = 0;
+constexpr uint32_t TM_EXT = 2 * BN;
+constexpr uint32_t TM_A = 2 * BN + 8;
+constexpr uint32_t TMEM_COLS = 512;
 
 struct ScreenSmem {
-  // byte offsets inside the 1024-aligned dynamic shared memory
-  uint32_t a, b, ring, bias, bars, total;
+  uint32_t slots, list, norm, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
+  uint32_t block_bytes, ext_off, slot_bytes, slot_tx;
+  int nslots;
 };
-__host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int BN, int nst) {
+__host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg) {
   ScreenSmem s;
+  const uint32_t rows = BN / cg;                    // codes of a tile held by one CTA
+  s.block_bytes = rows * 128;                       // one 64-dim block, 128B-swizzled
+  s.ext_off = dblk * s.block_bytes;                 // bias extension: [2 K-chunks][rows][16 B]
+  s.slot_tx = s.ext_off + rows * 32;
+  s.slot_bytes = (s.slot_tx + 1023u) & ~1023u;
+  const uint32_t fixed = LIST_BYTES + 2 * 2 * BM * 4 + 512;
+  int n = (int)((227u * 1024u - fixed) / s.slot_bytes);
+  s.nslots = n > MAX_SLOTS ? MAX_SLOTS : n;
   uint32_t off = 0;
-  s.a = off;    off += (uint32_t)dblk * A_BLOCK_BYTES;
-  s.b = off;    off += (uint32_t)nst * BN * BK * 2;
-  s.ring = off; off += 2u * LIST_BYTES;             // [group]{ [slot][row] float4 | [slot][row] u32 }
-  s.bias = off; off += 2u * 2u * BN * 4;            // [group][parity][BN]
-  s.bars = off; off += 512;
+  s.slots = off; off += (uint32_t)s.nslots * s.slot_bytes;
+  s.list = off;  off += LIST_BYTES;                 // { [entry][row] float4 | [entry][row] u32 }
+  s.norm = off;  off += 2 * 2 * BM * 4;             // [A buffer][loader half][row] partial ||z||^2
+  s.bars = off;  off += 512;
   s.total = off;
   return s;
 }
@@ -208,205 +316,255 @@ __device__ __noinline__ void list_compact(uint32_t sc_base, uint32_t co_base, ui
   pco = co_base + w * CO_STRIDE;
 }
 
-// TRACE: diagnostic instantiation (ccvsq_screen_trace) — CTA 0 records (clock64, event) pairs per role.
-#define CCVSQ_TRACE_EVENT(role, code)                                                            \
-  do {                                                                                           \
-    if (TRACE && blockIdx.x == 0 && trace_n[role] < 4000) {                                      \
-      trace[(role) * 4000 + trace_n[role]] = (clock64() << 8) | (long long)(code);               \
-      ++trace_n[role];                                                                           \
-    }                                                                                            \
-  } while (0)
+struct ScreenOut {
+  int64_t* idx;            // [N] final index of unambiguous rows (provisional best for queued rows)
+  int32_t* q_count;        // [1] rows queued for FP32 re-scoring
+  int32_t* q_rows;         // [N]
+  int32_t* q_cand;         // [N, n_cand]
+  uint8_t* q_flags;        // [N]
+  // diagnostics (all may be null)
+  int32_t* dbg_cand;       // [N, n_cand]
+  float* dbg_score;        // [N, n_cand]
+  uint8_t* dbg_flags;      // [N]
+  float* dbg_margin;       // [N]
+  float* dbg_scores;       // [N, K_pad]
+};
 
-template <int BN, int NST, bool TRACE>
+// 32 consecutive dims of one latent row -> registers (S == 1: contiguous row, else stride S)
+__device__ __forceinline__ void load_chunk(float (&v)[32], const float* __restrict__ p, int64_t S, bool valid) {
+  if (!valid) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    return;
+  }
+  if (S == 1) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(p4 + i);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __ldg(p + (int64_t)i * S);
+  }
+}
+
+template <int CG>
 __global__ void __launch_bounds__(SCREEN_THREADS, 1)
-screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-              const float* __restrict__ bias, const float* __restrict__ row_margin, int64_t N,
-              int num_row_tiles, int K, int K_pad, int dblk, int n_cand,
-              int32_t* __restrict__ cand_idx, float* __restrict__ cand_score,
-              uint8_t* __restrict__ flags, float* __restrict__ dbg_scores, long long* __restrict__ trace) {
-  int trace_n[4] = {0, 0, 0, 0};
-  (void)trace_n;
+screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_ext,
+              const float* __restrict__ z, const Lay L, const float* __restrict__ e_max, float margin_scale,
+              int K_pad, int n_tiles, int dblk, int n_cand, int num_group_tiles, const ScreenOut out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const ScreenSmem lay = screen_smem_layout(dblk, BN, NST);
+  const ScreenSmem lay = screen_smem_layout(dblk, CG);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_n_tiles = K_pad / BN;
-  constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
+  const uint32_t rank = (CG == 1) ? 0u : cluster_ctarank();
+  const int group = (int)blockIdx.x / CG, num_groups = (int)gridDim.x / CG;
+  const int nslots = lay.nslots;
+  const int abuf_n = dblk <= 4 ? 2 : 1;             // A buffers in tensor memory
+  const uint32_t a_cols = (uint32_t)dblk * 32;      // 32-bit columns per A buffer (D/2)
+  constexpr int ROWS = BN / CG;                     // codes of a tile in this CTA's shared memory
 
-  // barrier addresses
+  // barrier addresses (this CTA's copies; the leader's full / tmem_empty / a_full collect both CTAs)
   const uint32_t bar0 = smem_base + lay.bars;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (NST + s); };
-  auto tmem_full = [&](int b) { return bar0 + 8u * (2 * NST + b); };
-  auto tmem_empty = [&](int b) { return bar0 + 8u * (2 * NST + 2 + b); };
-  auto bias_rdy = [&](int g) { return bar0 + 8u * (2 * NST + 4 + g); };
-  // the stationary A tile is handed over per 64-dim block, so the next row tile's blocks stream in
-  // while the last code tile of the current row tile is still being multiplied
-  auto a_full = [&](int kb) { return bar0 + 8u * (2 * NST + 6 + kb); };
-  auto a_empty = [&](int kb) { return bar0 + 8u * (2 * NST + 14 + kb); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + lay.bars + 8u * (2 * NST + 22));
+  auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_SLOTS + s); };
+  auto tmem_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + b); };
+  auto tmem_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 2 + b); };
+  auto a_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 4 + b); };
+  auto a_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 6 + b); };
+  auto norm_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 8 + b); };
+  auto norm_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 10 + b); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + lay.bars + 8u * (2 * MAX_SLOTS + 12));
+  float* norm_s = reinterpret_cast<float*>(smem + lay.norm);
 
   if ((smem_base & 1023u) != 0) __trap();   // SWIZZLE_128B needs 1024-byte aligned tiles
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_ext);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int kb = 0; kb < 8; ++kb) { mbar_init(a_full(kb), 1); mbar_init(a_empty(kb), 1); }
+    for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full(b), 1);
-      mbar_init(tmem_empty(b), 128);
-      mbar_init(bias_rdy(b), 128);
+      mbar_init(tmem_empty(b), 4 * CG);     // one arrive per epilogue warp of every CTA in the group
+      mbar_init(a_full(b), 8 * CG);         // one arrive per loader warp of every CTA in the group
+      mbar_init(a_empty(b), 1);
+      mbar_init(norm_full(b), 8);
+      mbar_init(norm_empty(b), 4);
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 2) tmem_alloc<CG>(smem_u32(tmem_ptr_smem), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp >= 4 && warp < 8) {
+    // constant A block of the bias extension: (1, 1, 1, 0, ..., 0) in BF16, 16 K-elements = 8 columns
+    uint32_t ext[8] = {0x3F803F80u, 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u};
+    tmem_st8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TM_EXT, ext);
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer (every CTA: its half of each B tile) ===============
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, a_phase = 0;
-      for (int tile = blockIdx.x; tile < num_row_tiles; tile += gridDim.x) {
-        for (int j = 0; j < num_n_tiles; ++j) {
-          for (int kb = 0; kb < dblk; ++kb) {
-            if (j == 0) {   // A block kb of this row tile, as soon as the previous tile's MMAs released it
-              mbar_wait(a_empty(kb), a_phase ^ 1);
-              mbar_arrive_expect_tx(a_full(kb), A_BLOCK_BYTES);
-              tma_load_2d(smem_base + lay.a + kb * A_BLOCK_BYTES, &map_a, a_full(kb), kb * BK, tile * BM);
-            }
-            mbar_wait(empty_bar(stage), phase ^ 1);
-            CCVSQ_TRACE_EVENT(0, 1);                       // B stage issued
-            mbar_arrive_expect_tx(full_bar(stage), B_STAGE_BYTES);
-            tma_load_2d(smem_base + lay.b + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK,
-                        j * BN);
-            if (++stage == NST) { stage = 0; phase ^= 1; }
-          }
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int gt = group; gt < num_group_tiles; gt += num_groups) {
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(empty_bar(slot), phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(slot), lay.slot_tx * CG);
+          const uint32_t fb = (CG == 1) ? full_bar(slot) : mapa(full_bar(slot), 0);
+          const uint32_t dst = smem_base + lay.slots + (uint32_t)slot * lay.slot_bytes;
+          const int row0 = j * BN + (int)rank * ROWS;
+          for (int kb = 0; kb < dblk; ++kb)
+            tma_load_2d<CG>(dst + kb * lay.block_bytes, &map_b, fb, kb * 64, row0);
+          tma_load_2d<CG>(dst + lay.ext_off, &map_ext, fb, dblk * 64, row0);
+          tma_load_2d<CG>(dst + lay.ext_off + ROWS * 16, &map_ext, fb, dblk * 64 + 8, row0);
+          if (++slot == nslots) { slot = 0; phase ^= 1; }
         }
-        a_phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0, a_phase = 0;
-      uint32_t uses[2] = {0, 0};
-      for (int tile = blockIdx.x; tile < num_row_tiles; tile += gridDim.x) {
-        for (int j = 0; j < num_n_tiles; ++j) {
-          const int b = j & 1;
-          CCVSQ_TRACE_EVENT(1, 1);                         // start waiting for the accumulator buffer
-          mbar_wait(tmem_empty(b), (uses[b] & 1) ^ 1);
-          CCVSQ_TRACE_EVENT(1, 2);                         // accumulator buffer free
-          ++uses[b];
+    // =========================== MMA issuer (leader CTA) ===========================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
+      int slot = 0;
+      uint32_t phase = 0, acc_it = 0, tl = 0;
+      for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
+        const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
+        const uint32_t a_tmem = tmem_base + TM_A + ab * a_cols;
+        for (int j = 0; j < n_tiles; ++j, ++acc_it) {
+          const uint32_t b = acc_it & 1;
+          mbar_wait(tmem_empty(b), ((acc_it >> 1) & 1) ^ 1);
+          if (j == 0) mbar_wait(a_full(ab), a_phase);
+          mbar_wait(full_bar(slot), phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
+          const uint32_t d_tmem = tmem_base + TM_ACC + b * BN;
+          const uint32_t sbase = smem_base + lay.slots + (uint32_t)slot * lay.slot_bytes;
+          // bias first (overwrites the accumulator), then the D/16 K steps of the dot product
+          umma_ts<CG>(d_tmem, tmem_base + TM_EXT, make_nosw_desc(sbase + lay.ext_off, ROWS * 16), idesc, 0u);
           for (int kb = 0; kb < dblk; ++kb) {
-            if (j == 0) mbar_wait(a_full(kb), a_phase);
-            mbar_wait(full_bar(stage), phase);
-            CCVSQ_TRACE_EVENT(1, 3);                       // operands of this k-block landed
-            tc_fence_after();
-            const uint32_t a_addr = smem_base + lay.a + kb * A_BLOCK_BYTES;
-            const uint32_t b_addr = smem_base + lay.b + stage * B_STAGE_BYTES;
+            const uint32_t b_addr = sbase + kb * lay.block_bytes;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t da = make_sw128_desc(a_addr + k * 32);
-              const uint64_t db = make_sw128_desc(b_addr + k * 32);
-              umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(empty_bar(stage));      // smem stage reusable once these MMAs retire
-            if (j == num_n_tiles - 1) umma_commit(a_empty(kb));   // last reader of A block kb
-            if (++stage == NST) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < 4; ++k)
+              umma_ts<CG>(d_tmem, a_tmem + kb * 32 + k * 8, make_sw128_desc(b_addr + k * 32), idesc, 1u);
           }
-          umma_commit(tmem_full(b));            // accumulator tile j complete
-          CCVSQ_TRACE_EVENT(1, 4);                         // tile issued
+          umma_commit<CG>(empty_bar(slot));      // B slot reusable once these MMAs retire
+          umma_commit<CG>(tmem_full(b));         // accumulator tile complete
+          if (j == n_tiles - 1) umma_commit<CG>(a_empty(ab));   // last reader of this A buffer
+          if (++slot == nslots) { slot = 0; phase ^= 1; }
         }
-        a_phase ^= 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // =========================== A loaders: FP32 global -> BF16 -> tensor memory ================
+    const int q = warp & 3, h = (warp - 8) >> 2;
+    const int r = q * 32 + lane;
+    const int half = dblk * 32;                 // dims handled by this loader half
+    const int nchunk = dblk;                    // chunks of 32 dims
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + TM_A + (uint32_t)(h * half / 2);
+    const uint32_t af_bar = (CG == 1) ? a_full(0) : mapa(a_full(0), 0);
+    uint32_t tl = 0;
+    for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
+      const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
+      const int64_t n = ((int64_t)gt * CG + rank) * BM + r;
+      const bool valid = n < L.N;
+      const float* p = z;
+      if (valid) {
+        const int64_t pos = n / L.mult;
+        const int m = (int)(n - pos * L.mult);
+        p = z + pos_base(L, pos) + ((int64_t)m * L.D + (int64_t)h * half) * L.S;
+      }
+      float va[32], vb[32];
+      load_chunk(va, p, L.S, valid);            // in flight while waiting for the buffer
+      mbar_wait(a_empty(ab), a_phase ^ 1);
+      tc_fence_after();
+      float ss = 0.f;
+      const uint32_t dst = lane_base + ab * a_cols;
+      for (int c = 0; c < nchunk; c += 2) {
+        if (c + 1 < nchunk) load_chunk(vb, p + (int64_t)(c + 1) * 32 * L.S, L.S, valid);
+        {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            ss = fmaf(va[2 * i], va[2 * i], ss);
+            ss = fmaf(va[2 * i + 1], va[2 * i + 1], ss);
+            __nv_bfloat162 t = __floats2bfloat162_rn(va[2 * i], va[2 * i + 1]);   // .x (low half) = even k
+            pk[i] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          tmem_st16(dst + c * 16, pk);
+        }
+        if (c + 1 < nchunk) {
+          if (c + 2 < nchunk) load_chunk(va, p + (int64_t)(c + 2) * 32 * L.S, L.S, valid);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            ss = fmaf(vb[2 * i], vb[2 * i], ss);
+            ss = fmaf(vb[2 * i + 1], vb[2 * i + 1], ss);
+            __nv_bfloat162 t = __floats2bfloat162_rn(vb[2 * i], vb[2 * i + 1]);
+            pk[i] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          tmem_st16(dst + (c + 1) * 16, pk);
+        }
+      }
+      tmem_st_wait();
+      mbar_wait(norm_empty(ab), a_phase ^ 1);   // the epilogue has read the previous norms of this buffer
+      norm_s[(ab * 2 + h) * BM + r] = ss;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(norm_full(ab));
+        if (CG == 1) mbar_arrive(a_full(ab)); else mbar_arrive_cluster(af_bar + 8u * ab);
       }
     }
   } else if (warp >= 4) {
-    // =========================== epilogue groups ===========================
-    // The two groups are fully decoupled: group g owns the code tiles j == g (mod 2) and the TMEM
-    // buffer g, keeps its own running maximum and candidate list and writes its own half of the
-    // output; ccvsq_rescore merges the two halves.
-    const int g = (warp - 4) >> 2;             // 0: even code tiles, 1: odd code tiles
-    const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    // =========================== epilogue: one latent row per thread, all codes =================
+    const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
-    const int tg = threadIdx.x - 128 - g * 128;   // 0..127 inside the group
-    float* bias_s = reinterpret_cast<float*>(smem + lay.bias) + g * 2 * BN;
-    const uint32_t sc_base = smem_base + lay.ring + (uint32_t)g * LIST_BYTES + (uint32_t)row_in_tile * 16u;
-    const uint32_t co_base = smem_base + lay.ring + (uint32_t)g * LIST_BYTES + LCAP * SC_STRIDE + (uint32_t)row_in_tile * 4u;
+    const uint32_t sc_base = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
+    const uint32_t co_base = smem_base + lay.list + LCAP * SC_STRIDE + (uint32_t)row_in_tile * 4u;
     const uint32_t co_limit = co_base + (LCAP - 2) * CO_STRIDE;   // appending 2 groups needs pco <= co_limit
-    uint32_t full_phase = 0;
-    uint32_t it = 0;                           // tiles processed by this group (bias buffer parity)
-    const bool has_tiles = g < num_n_tiles;
+    const uint32_t te_bar = (CG == 1) ? tmem_empty(0) : mapa(tmem_empty(0), 0);
+    const float emax = e_max ? __ldg(e_max) : 1.f;
+    uint32_t acc_it = 0, tl = 0;
 
-    // bias of the next tile this group will process, prefetched one tile ahead (also across row tiles)
-    float nb[BN / 128];
-    if (has_tiles && (int)blockIdx.x < num_row_tiles) {
-#pragma unroll
-      for (int u = 0; u < BN / 128; ++u) nb[u] = __ldg(bias + (size_t)g * BN + u * 128 + tg);
-    }
-
-    for (int tile = blockIdx.x; tile < num_row_tiles; tile += gridDim.x) {
-      const int64_t row = (int64_t)tile * BM + row_in_tile;
-      const float margin = __ldg(row_margin + row);
+    for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
+      const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
+      const int64_t row = ((int64_t)gt * CG + rank) * BM + row_in_tile;
+      mbar_wait(norm_full(ab), a_phase);
+      const float margin = margin_scale * emax * sqrtf(norm_s[(ab * 2) * BM + row_in_tile] + norm_s[(ab * 2 + 1) * BM + row_in_tile]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(norm_empty(ab));
       float runmax = -FLT_MAX;
       float dropped_max = -FLT_MAX;
       uint32_t psc = sc_base, pco = co_base;    // next free list entry
 
-      for (int j = g; j < num_n_tiles; j += 2, ++it) {
-        float* bs = bias_s + (it & 1) * BN;
-#pragma unroll
-        for (int u = 0; u < BN / 128; ++u) bs[u * 128 + tg] = nb[u];
-        mbar_arrive(bias_rdy(g));               // (waited on below, after the accumulator wait)
-        {
-          int jn = j + 2;                       // next tile of this group: same row tile, or the
-          if (jn >= num_n_tiles) jn = g;        // first one of the next row tile
-          if (j + 2 < num_n_tiles || tile + (int)gridDim.x < num_row_tiles) {
-#pragma unroll
-            for (int u = 0; u < BN / 128; ++u) nb[u] = __ldg(bias + (size_t)jn * BN + u * 128 + tg);
-          }
-        }
-        if (tg == 0) CCVSQ_TRACE_EVENT(2 + g, 1);          // waiting for accumulator tile
-        mbar_wait(tmem_full(g), full_phase);
-        full_phase ^= 1;
+      for (int j = 0; j < n_tiles; ++j, ++acc_it) {
+        const uint32_t b = acc_it & 1;
+        mbar_wait(tmem_full(b), (acc_it >> 1) & 1);
         tc_fence_after();
-        mbar_wait(bias_rdy(g), it & 1);
-        if (tg == 0) CCVSQ_TRACE_EVENT(2 + g, 2);          // tile available         // all 128 threads of the group stored their bias slice
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + b * BN;
         const int col0 = j * BN;
 
-        // One 32-column chunk of this thread's row.  Fast path: bias add + max tree (FMNMX3).  A
-        // chunk can only contribute candidates if its maximum reaches (running max - margin); then
-        // the threshold is refreshed and every group of 4 columns whose maximum reaches it is
-        // appended (its 4 raw scores + first code) with predicated, branch-free stores.
+        // One 32-column chunk of this thread's row.  Fast path: a max tree (FMNMX3).  A chunk can
+        // only contribute candidates if its maximum reaches (running max - margin); then the
+        // threshold is refreshed and every group of 4 columns whose maximum reaches it is appended
+        // (its 4 raw scores + first code) with predicated, branch-free stores.
         auto process = [&](uint32_t (&ra)[32], const int cbase) {
           float v[32];
-          const float4* b4 = reinterpret_cast<const float4*>(bs + cbase);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bb = b4[i];
-            v[4 * i + 0] = __uint_as_float(ra[4 * i + 0]) + bb.x;
-            v[4 * i + 1] = __uint_as_float(ra[4 * i + 1]) + bb.y;
-            v[4 * i + 2] = __uint_as_float(ra[4 * i + 2]) + bb.z;
-            v[4 * i + 3] = __uint_as_float(ra[4 * i + 3]) + bb.w;
-          }
-          if (dbg_scores) {   // diagnostic dump of the raw score tile (ccvsq_screen_dump only)
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
+          if (out.dbg_scores && row < L.N) {   // diagnostic dump of the raw score tile
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dbg_scores[row * K_pad + col0 + cbase + i] = v[i];
+            for (int i = 0; i < 32; ++i) out.dbg_scores[row * K_pad + col0 + cbase + i] = v[i];
           }
           float m4[8];
 #pragma unroll
@@ -441,28 +599,29 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           }
         };
 
-        // two 32-column chunks in flight: the tcgen05.ld of chunk c+1 overlaps the arithmetic on chunk c
+        // three 32-column chunks; the tcgen05.ld of the next chunk overlaps the max tree of this one,
+        // and the accumulator is handed back as soon as the last chunk is in registers
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr0, ra);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; c += 2) {
-          tmem_ld_wait();
-          tmem_ld32(taddr0 + (c + 1) * 32, rb);
-          process(ra, c * 32);
-          tmem_ld_wait();
-          if (c + 2 < BN / 32) tmem_ld32(taddr0 + (c + 2) * 32, ra);
-          process(rb, (c + 1) * 32);
-        }
+        tmem_ld_wait();
+        tmem_ld32(taddr0 + 32, rb);
+        process(ra, 0);
+        tmem_ld_wait();
+        tmem_ld32(taddr0 + 64, ra);
+        process(rb, 32);
+        tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(tmem_empty(g));
-        if (tg == 0) CCVSQ_TRACE_EVENT(2 + g, 3);          // tile consumed
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
+        }
+        process(ra, 64);
       }
 
-      // ---- this group's candidates for the row: every listed code with score >= runmax - margin,
-      //      sorted by (score desc, code asc), at most n_cand of them.  The list is in increasing
-      //      code order, so a strict '>' scan keeps the lowest code among equal scores.
-      if (row < N) {
-        const int64_t obase = (row * 2 + g) * n_cand;
+      // ---- candidates of the row: every listed code with score >= runmax - margin, sorted by
+      //      (score desc, code asc), at most n_cand of them.  The list is in increasing code order,
+      //      so a strict '>' scan keeps the lowest code among equal scores.
+      if (row < L.N) {
         const float thr = runmax - margin;
         const uint32_t n = (pco - co_base) / CO_STRIDE;
         uint32_t within = 0;
@@ -474,26 +633,28 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {      // branch-free (padding codes carry -inf and never pass)
+          for (int u = 0; u < 4; ++u) {      // branch-free (padding codes carry -3e38 and never pass)
             within += (sc[u] >= thr) ? 1u : 0u;
             const bool better = sc[u] > best_s;
             best_s = better ? sc[u] : best_s;
             best_i = better ? (int)code + u : best_i;
           }
         }
-        if (within <= 1 && n_cand == 4) {   // the overwhelmingly common case: two 16-byte stores
-          *reinterpret_cast<int4*>(cand_idx + obase) = make_int4(within ? best_i : -1, -1, -1, -1);
-          *reinterpret_cast<float4*>(cand_score + obase) = make_float4(best_s, -INFINITY, -INFINITY, -INFINITY);
-        } else {
-          int written = 0;
-          if (within >= 1) {
-            cand_idx[obase] = best_i;
-            cand_score[obase] = best_s;
-            written = 1;
-          }
+        const uint8_t flag = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped_max >= thr ? 2 : 0));
+        const bool final_row = within == 1 && flag == 0;
+        const bool want_list = !final_row || out.dbg_cand;
+        int cand[CCVSQ_MAX_CAND];
+        float cscore[CCVSQ_MAX_CAND];
+#pragma unroll
+        for (int c = 0; c < CCVSQ_MAX_CAND; ++c) { cand[c] = -1; cscore[c] = -INFINITY; }
+        cand[0] = best_i;
+        cscore[0] = best_s;
+        if (want_list && within > 1) {      // near-ties: repeated selection
           float prev_s = best_s;
           int prev_i = best_i;
-          for (int c = 1; c < n_cand && within > 1; ++c) {   // near-ties: repeated selection
+#pragma unroll
+          for (int c = 1; c < CCVSQ_MAX_CAND; ++c) {
+            if (c >= n_cand || prev_i == 0x7fffffff) continue;
             float bs_ = -INFINITY;
             int bi = 0x7fffffff;
             for (uint32_t e = 0; e < n; ++e) {
@@ -510,30 +671,39 @@ screen_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 if (x >= thr && after_prev && better) { bs_ = x; bi = i; }
               }
             }
-            if (bi == 0x7fffffff) break;
-            cand_idx[obase + c] = bi;
-            cand_score[obase + c] = bs_;
             prev_s = bs_;
             prev_i = bi;
-            ++written;
-          }
-          for (int c = written; c < n_cand; ++c) {
-            cand_idx[obase + c] = -1;
-            cand_score[obase + c] = -INFINITY;
+            if (bi != 0x7fffffff) { cand[c] = bi; cscore[c] = bs_; }
           }
         }
-        if (tg == 0) CCVSQ_TRACE_EVENT(2 + g, 4);          // row tile finalised
-        flags[row * 2 + g] = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped_max >= thr ? 2 : 0));
+        if (out.idx) out.idx[row] = best_i;
+        if (!final_row && out.q_count) {
+          const int slot = atomicAdd(out.q_count, 1);
+          out.q_rows[slot] = (int32_t)row;
+          out.q_flags[slot] = flag;
+#pragma unroll
+          for (int c = 0; c < CCVSQ_MAX_CAND; ++c)
+            if (c < n_cand) out.q_cand[(int64_t)slot * n_cand + c] = cand[c];
+        }
+        if (out.dbg_cand) {
+#pragma unroll
+          for (int c = 0; c < CCVSQ_MAX_CAND; ++c)
+            if (c < n_cand) {
+              out.dbg_cand[row * n_cand + c] = cand[c];
+              out.dbg_score[row * n_cand + c] = cscore[c];
+            }
+          out.dbg_flags[row] = flag;
+          out.dbg_margin[row] = margin;
+        }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
-                 : "memory");
+    tmem_dealloc<CG>(tmem_base, TMEM_COLS);
   }
 }
 
@@ -559,35 +729,55 @@ static int get_encode_fn(EncodeTiledFn* out) {
   return CCVSQ_OK;
 }
 
-// row-major [rows, D] BF16, box = 64 columns x box_rows rows, 128-byte swizzle
-static int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int64_t rows, int D,
-                    int box_rows) {
-  cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+// codebook shadow: row-major [rows, D + 16] BF16; box = box_cols columns x box_rows rows
+static int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int64_t rows, int cols_total,
+                    int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+  cuuint64_t gdim[2] = {(cuuint64_t)cols_total, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols_total * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CCVSQ_REQUIRE(r == CUDA_SUCCESS, CCVSQ_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d",
                 (int)r);
   return CCVSQ_OK;
 }
 
-template <int BN, int NST, bool TRACE = false>
-static int launch_screen(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias,
-                         const float* row_margin, int64_t N, int tiles, int K, int K_pad, int dblk,
-                         int n_cand, int32_t* cand_idx, float* cand_score, uint8_t* flags,
-                         float* dbg_scores, cudaStream_t st, long long* trace = nullptr) {
-  const ScreenSmem lay = screen_smem_layout(dblk, BN, NST);
-  const size_t smem = lay.total;
-  CCVSQ_REQUIRE(smem <= 227 * 1024, CCVSQ_UNSUPPORTED, "screen: %zu bytes of shared memory needed", smem);
-  auto kern = screen_kernel<BN, NST, TRACE>;
-  if (int rc = enable_smem(kern, smem)) return rc;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  kern<<<grid, SCREEN_THREADS, smem, st>>>(ma, mb, bias, row_margin, N, tiles, K, K_pad, dblk, n_cand,
-                                         cand_idx, cand_score, flags, dbg_scores, trace);
-  CCVSQ_LAUNCH_CHECK();
+template <int CG>
+static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const float* e_max,
+                         float margin_scale, int K_pad, int D, int n_cand, const ScreenOut& out,
+                         cudaStream_t st) {
+  const int dblk = D / 64;
+  const ScreenSmem lay = screen_smem_layout(dblk, CG);
+  CCVSQ_REQUIRE(lay.nslots >= 2, CCVSQ_UNSUPPORTED, "screen: D=%d leaves room for %d B slots", D, lay.nslots);
+  EncodeTiledFn enc;
+  if (int rc = get_encode_fn(&enc)) return rc;
+  CUtensorMap mb, mx;
+  if (int rc = make_map(enc, &mb, E_bf16, K_pad, D + SCREEN_EXT, 64, BN / CG, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  if (int rc = make_map(enc, &mx, E_bf16, K_pad, D + SCREEN_EXT, 8, BN / CG, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  auto kern = screen_kernel<CG>;
+  if (int rc = enable_smem(kern, lay.total)) return rc;
+  const int64_t rows_per_group = (int64_t)BM * CG;
+  const int64_t group_tiles = (L.N + rows_per_group - 1) / rows_per_group;
+  CCVSQ_REQUIRE(group_tiles < (1ll << 24), CCVSQ_BAD_SHAPE, "screen: N=%lld too large for one launch",
+                (long long)L.N);
+  const int max_groups = kNumSMs / CG;
+  const int groups = (int)(group_tiles < max_groups ? group_tiles : max_groups);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(SCREEN_THREADS);
+  cfg.dynamicSmemBytes = lay.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CCVSQ_CUDA(cudaLaunchKernelEx(&cfg, kern, mb, mx, z, L, e_max, margin_scale, K_pad, K_pad / BN, dblk, n_cand,
+                                (int)group_tiles, out));
   return CCVSQ_OK;
 }
 
@@ -595,63 +785,63 @@ static int launch_screen(const CUtensorMap& ma, const CUtensorMap& mb, const flo
 
 using namespace ccvsq;
 
-static int screen_impl(const void* z_bf16, const float* row_margin, const void* E_bf16, const float* bias,
-                       int64_t N, int K, int D, int n_cand, int32_t* cand_idx, float* cand_score,
-                       uint8_t* flags, float* dbg_scores, void* stream, long long* trace = nullptr) {
-  CCVSQ_REQUIRE(z_bf16 && row_margin && E_bf16 && bias && cand_idx && cand_score && flags,
-                CCVSQ_NULL_POINTER, "screen: null pointer");
-  CCVSQ_REQUIRE(N > 0 && K > 0, CCVSQ_BAD_SHAPE, "screen: N=%lld K=%d", (long long)N, K);
+static int screen_impl(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
+                       float margin_tau, int n_cand, const ScreenOut& out, int cta_group, void* stream) {
+  CCVSQ_REQUIRE(z && E_bf16, CCVSQ_NULL_POINTER, "screen: null pointer");
+  CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "screen: K=%d", K);
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  const int D = L.D;
   CCVSQ_REQUIRE(D % 64 == 0 && D >= 64 && D <= 512, CCVSQ_UNSUPPORTED,
                 "screen: D=%d unsupported by the tensor-core path (need 64 <= D <= 512, D %% 64 == 0)", D);
   CCVSQ_REQUIRE(n_cand >= 1 && n_cand <= CCVSQ_MAX_CAND, CCVSQ_BAD_SHAPE, "screen: n_cand=%d", n_cand);
-  CCVSQ_REQUIRE((((uintptr_t)z_bf16 | (uintptr_t)E_bf16 | (uintptr_t)cand_idx | (uintptr_t)cand_score) & 15) == 0,
-                CCVSQ_MISALIGNED, "screen: BF16 operands and candidate arrays must be 16-byte aligned");
-  const int64_t N_pad = ((N + BM - 1) / BM) * BM;
-  const int K_pad = ((K + 255) / 256) * 256;
-  const int64_t tiles64 = N_pad / BM;
-  CCVSQ_REQUIRE(tiles64 < (1ll << 24), CCVSQ_BAD_SHAPE, "screen: N=%lld too large for one launch",
-                (long long)N);
-  const int dblk = D / 64;
-  EncodeTiledFn enc;
-  if (int rc = get_encode_fn(&enc)) return rc;
-  CUtensorMap ma, mb;
-  if (int rc = make_map(enc, &ma, z_bf16, N_pad, D, BM)) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (dblk <= 4) {
-    if (int rc = make_map(enc, &mb, E_bf16, K_pad, D, 256)) return rc;
-    if (trace)
-      return launch_screen<256, 4, true>(ma, mb, bias, row_margin, N, (int)tiles64, K, K_pad, dblk, n_cand,
-                                         cand_idx, cand_score, flags, dbg_scores, st, trace);
-    return launch_screen<256, 4>(ma, mb, bias, row_margin, N, (int)tiles64, K, K_pad, dblk, n_cand,
-                                 cand_idx, cand_score, flags, dbg_scores, st);
-  }
-  if (int rc = make_map(enc, &mb, E_bf16, K_pad, D, 128)) return rc;
-  return launch_screen<128, 4>(ma, mb, bias, row_margin, N, (int)tiles64, K, K_pad, dblk, n_cand, cand_idx,
-                               cand_score, flags, dbg_scores, st);
+  CCVSQ_REQUIRE(L.N < (1ll << 31), CCVSQ_BAD_SHAPE, "screen: N=%lld rows exceed int32 row ids", (long long)L.N);
+  CCVSQ_REQUIRE((((uintptr_t)z | (uintptr_t)E_bf16) & 15) == 0, CCVSQ_MISALIGNED,
+                "screen: z and the codebook shadow must be 16-byte aligned");
+  CCVSQ_REQUIRE(cta_group == 1 || cta_group == 2, CCVSQ_BAD_SHAPE, "screen: cta_group=%d", cta_group);
+  const int K_pad = ccvsq_codebook_rows(K);
+  const float margin_scale = margin_tau * 0.00390625f;   // tau * 2^-8
+  if (cta_group == 2)
+    return launch_screen<2>(E_bf16, z, L, e_max, margin_scale, K_pad, D, n_cand, out, (cudaStream_t)stream);
+  return launch_screen<1>(E_bf16, z, L, e_max, margin_scale, K_pad, D, n_cand, out, (cudaStream_t)stream);
 }
 
-extern "C" int ccvsq_screen(const void* z_bf16, const float* row_margin, const void* E_bf16,
-                            const float* bias, int64_t N, int K, int D, int n_cand, int32_t* cand_idx,
-                            float* cand_score, uint8_t* flags, void* stream) {
-  return screen_impl(z_bf16, row_margin, E_bf16, bias, N, K, D, n_cand, cand_idx, cand_score, flags, nullptr,
-                     stream);
+extern "C" int ccvsq_codebook_rows(int K) { return (K + SCREEN_BN - 1) / SCREEN_BN * SCREEN_BN; }
+
+extern "C" int ccvsq_screen(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
+                            float margin_tau, int n_cand, int64_t* idx, int32_t* queue_count,
+                            int32_t* queue_rows, int32_t* queue_cand, uint8_t* queue_flags, void* stream) {
+  CCVSQ_REQUIRE(idx && queue_count && queue_rows && queue_cand && queue_flags, CCVSQ_NULL_POINTER,
+                "screen: null output pointer");
+  ScreenOut out = {};
+  out.idx = idx;
+  out.q_count = queue_count;
+  out.q_rows = queue_rows;
+  out.q_cand = queue_cand;
+  out.q_flags = queue_flags;
+  return screen_impl(z, lay, E_bf16, e_max, K, margin_tau, n_cand, out, 2, stream);
 }
 
-extern "C" int ccvsq_screen_dump(const void* z_bf16, const float* row_margin, const void* E_bf16,
-                                 const float* bias, int64_t N, int K, int D, int n_cand, int32_t* cand_idx,
-                                 float* cand_score, uint8_t* flags, float* scores, void* stream) {
-  CCVSQ_REQUIRE(scores, CCVSQ_NULL_POINTER, "screen_dump: scores must be non-null");
-  return screen_impl(z_bf16, row_margin, E_bf16, bias, N, K, D, n_cand, cand_idx, cand_score, flags, scores,
-                     stream);
-}
-
-// Diagnostic: CTA 0 records a per-role event timeline, trace is int64 [4][4000] zero-filled by the
-// caller (roles: 0 TMA producer, 1 MMA issuer, 2/3 epilogue groups; value = clock64 << 8 | event).
-extern "C" int ccvsq_screen_trace(const void* z_bf16, const float* row_margin, const void* E_bf16,
-                                  const float* bias, int64_t N, int K, int D, int n_cand, int32_t* cand_idx,
-                                  float* cand_score, uint8_t* flags, long long* trace, void* stream) {
-  CCVSQ_REQUIRE(trace, CCVSQ_NULL_POINTER, "screen_trace: trace must be non-null");
-  CCVSQ_REQUIRE(D <= 256, CCVSQ_UNSUPPORTED, "screen_trace: only the BN=256 configuration is traced");
-  return screen_impl(z_bf16, row_margin, E_bf16, bias, N, K, D, n_cand, cand_idx, cand_score, flags, nullptr,
-                     stream, trace);
+extern "C" int ccvsq_screen_debug(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max,
+                                  int K, float margin_tau, int n_cand, int cta_group, int64_t* idx,
+                                  int32_t* queue_count, int32_t* queue_rows, int32_t* queue_cand,
+                                  uint8_t* queue_flags, int32_t* cand_idx, float* cand_score, uint8_t* flags,
+                                  float* row_margin, float* scores, void* stream) {
+  CCVSQ_REQUIRE(cand_idx && cand_score && flags && row_margin, CCVSQ_NULL_POINTER,
+                "screen_debug: candidate dump pointers must be non-null");
+  CCVSQ_REQUIRE((queue_count == nullptr) == (queue_rows == nullptr) && (queue_count == nullptr) == (queue_cand == nullptr) &&
+                    (queue_count == nullptr) == (queue_flags == nullptr),
+                CCVSQ_NULL_POINTER, "screen_debug: queue pointers must be given together");
+  ScreenOut out = {};
+  out.idx = idx;
+  out.q_count = queue_count;
+  out.q_rows = queue_rows;
+  out.q_cand = queue_cand;
+  out.q_flags = queue_flags;
+  out.dbg_cand = cand_idx;
+  out.dbg_score = cand_score;
+  out.dbg_flags = flags;
+  out.dbg_margin = row_margin;
+  out.dbg_scores = scores;
+  return screen_impl(z, lay, E_bf16, e_max, K, margin_tau, n_cand, out, cta_group, stream);
 }

@@ -1,5 +1,5 @@
 // stream_kernels.cu — the HBM-bound kernels of the quantizer path (everything except the
-// tcgen05 screening GEMM): codebook preparation, latent packing, FP32 rescoring, assignment
+// tcgen05 screening GEMM): codebook preparation, FP32 rescoring of queued rows, assignment
 // (gather + straight-through value + squared error), decode gather, backward, per-code
 // scatter-reduce, finalize, EMA update.
 //
@@ -76,175 +76,109 @@ __device__ __forceinline__ void tile_store(float* __restrict__ out, const float*
 static inline size_t tile_smem_bytes(const Lay& L) { return (size_t)PT * (L.C + 1) * sizeof(float); }
 
 // ------------------------------------------------------------------------------------------------
-// prepare_codebook: one warp per (padded) code row
+// prepare_codebook: one warp per (padded) code row.  BF16 shadow row = [ bf16(e_0..e_{D-1}) |
+// hi, mid, lo, 0 x 13 ] where hi+mid+lo is a 3-term BF16 split of the bias -0.5||e||^2 (exact to
+// FP32): the screen multiplies these 16 extra columns with a constant (1,1,1,0,...) block, so the
+// tensor-core accumulator already holds z.e - 0.5||e||^2.  Padding rows carry a bias of -3e38.
 // ------------------------------------------------------------------------------------------------
 __global__ void prepare_codebook_kernel(const float* __restrict__ E, int K, int K_pad, int D,
                                         float* __restrict__ e_sq, __nv_bfloat16* __restrict__ Eb,
-                                        float* __restrict__ bias, unsigned int* __restrict__ e_max_bits) {
+                                        unsigned int* __restrict__ e_max_bits) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K_pad) return;
-  if (k >= K) {
-    if (Eb)
-      for (int j = lane; j < D; j += 32) Eb[(size_t)k * D + j] = __float2bfloat16_rn(0.f);
-    if (bias && lane == 0) bias[k] = -INFINITY;
-    return;
-  }
-  const float* e = E + (size_t)k * D;
+  const int DE = D + SCREEN_EXT;
   float acc = 0.f;
-  for (int j = lane; j < D; j += 32) {
-    float v = e[j];
-    acc = fmaf(v, v, acc);
-    if (Eb) Eb[(size_t)k * D + j] = __float2bfloat16_rn(v);
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    e_sq[k] = acc;
-    if (bias) bias[k] = -0.5f * acc;
-    if (e_max_bits) atomicMax(e_max_bits, __float_as_uint(sqrtf(acc)));  // acc >= 0: uint order == float order
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// pack_latents: any layout -> row-major bf16 [N_pad, D] + per-row margin
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) pack_latents_kernel(const float* __restrict__ z, Lay L,
-                                                          __nv_bfloat16* __restrict__ zb,
-                                                          float* __restrict__ row_margin,
-                                                          float margin_scale,
-                                                          const float* __restrict__ e_max,
-                                                          int64_t N_pad) {
-  extern __shared__ float tile[];
-  if (e_max) margin_scale *= __ldg(e_max);
-  const int CP = L.C + 1;
-  const int64_t p0 = (int64_t)blockIdx.x * PT;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows_per_tile = PT * L.mult;
-  const int64_t n0 = p0 * L.mult;
-  if (p0 >= L.P) {
-    // pure padding tile: zero rows [n0, min(n0 + rows, N_pad))
-    for (int r = warp; r < rows_per_tile; r += NW) {
-      int64_t n = n0 + r;
-      if (n >= N_pad) break;
-      for (int j = lane; j < L.D; j += 32) zb[n * L.D + j] = __float2bfloat16_rn(0.f);
-      if (lane == 0) row_margin[n] = 0.f;
+  if (k < K) {
+    const float* e = E + (size_t)k * D;
+    for (int j = lane; j < D; j += 32) {
+      float v = e[j];
+      acc = fmaf(v, v, acc);
+      if (Eb) Eb[(size_t)k * DE + j] = __float2bfloat16_rn(v);
     }
-    return;
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      e_sq[k] = acc;
+      if (e_max_bits) atomicMax(e_max_bits, __float_as_uint(sqrtf(acc)));  // acc >= 0: uint order == float order
+    }
+  } else if (Eb) {
+    for (int j = lane; j < D; j += 32) Eb[(size_t)k * DE + j] = __float2bfloat16_rn(0.f);
   }
-  const int np = (int)min((int64_t)PT, L.P - p0);
-  tile_load(z, L, p0, np, tile);
-  __syncthreads();
-  for (int r = warp; r < rows_per_tile; r += NW) {
-    const int64_t n = n0 + r;
-    if (n >= N_pad) break;
-    const int p = r / L.mult, m = r - p * L.mult;
-    if (p < np) {
-      const float* t = tile + p * CP + m * L.D;
-      float acc = 0.f;
-      for (int j = lane; j < L.D; j += 32) {
-        float v = t[j];
-        acc = fmaf(v, v, acc);
-        zb[n * L.D + j] = __float2bfloat16_rn(v);
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) row_margin[n] = margin_scale * sqrtf(acc);
+  if (Eb && lane < SCREEN_EXT) {
+    float t = 0.f;
+    if (k >= K) {
+      t = lane == 0 ? -3.0e38f : 0.f;
     } else {
-      for (int j = lane; j < L.D; j += 32) zb[n * L.D + j] = __float2bfloat16_rn(0.f);
-      if (lane == 0) row_margin[n] = 0.f;
+      const float bias = -0.5f * acc;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(bias);
+      const float r1 = bias - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(mid);
+      t = lane == 0 ? __bfloat162float(hi) : lane == 1 ? __bfloat162float(mid) : lane == 2 ? r2 : 0.f;
     }
+    Eb[(size_t)k * DE + D + lane] = __float2bfloat16_rn(t);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// rescore: merge the two epilogue groups' candidate lists, then FP32 re-evaluation of the survivors
-// (reference formula, lowest-index ties).  cand/score are [N][2][n_cand]; an entry is live if its
-// code is >= 0 and its BF16 score is within the row margin of the better of the two group maxima.
+// rescore: FP32 re-evaluation of the rows the screen queued (more than one code inside the margin),
+// reference formula and lowest-index tie-break.  One warp per queued row; the queue length is read
+// on the device.  Rows whose candidate set is incomplete (flags != 0) go to the exact fallback.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) rescore_kernel(const float* __restrict__ z, Lay L,
-                                                     const float* __restrict__ E,
-                                                     const float* __restrict__ e_sq, int K,
-                                                     const int32_t* __restrict__ cand,
-                                                     const float* __restrict__ score,
-                                                     const float* __restrict__ row_margin, int n_cand,
-                                                     const uint8_t* __restrict__ flags,
-                                                     int64_t* __restrict__ idx,
-                                                     int64_t* __restrict__ fb_rows,
-                                                     int32_t* __restrict__ fb_count, int64_t fb_cap) {
-  extern __shared__ float tile[];
-  __shared__ int need_tile;
-  const int CP = L.C + 1;
-  const int nc2 = 2 * n_cand;
-  const int64_t p0 = (int64_t)blockIdx.x * PT;
-  const int np = (int)min((int64_t)PT, L.P - p0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows = np * L.mult;
-  const int64_t n0 = p0 * L.mult;
-
-  // Pass 0: rows with exactly one live candidate are final; find out whether the tile needs z at all.
-  if (threadIdx.x == 0) need_tile = 0;
-  __syncthreads();
-  for (int r = threadIdx.x; r < rows; r += NT) {
-    const int64_t n = n0 + r;
-    const int32_t* cr = cand + n * nc2;
-    const float* sr = score + n * nc2;
-    const float thr = fmaxf(sr[0], sr[n_cand]) - row_margin[n];   // slot 0 of each half = group maximum
-    int live = 0, only = -1;
-    for (int c = 0; c < nc2; ++c) {
-      const int k = cr[c];
-      if (k >= 0 && sr[c] >= thr) { ++live; only = k; }
-    }
-    if (live == 1) idx[n] = only;
-    else need_tile = 1;
-    // a half's list is incomplete w.r.t. the GLOBAL threshold if it was truncated (bit0) and its last
-    // slot is still live, or if it dropped entries (bit1) while its maximum is live
-    bool incomplete = false;
-    if (flags) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint8_t f = flags[2 * n + h];
-        incomplete |= (f & 1) && cr[h * n_cand + n_cand - 1] >= 0 && sr[h * n_cand + n_cand - 1] >= thr;
-        incomplete |= (f & 2) && sr[h * n_cand] >= thr;
+__global__ void __launch_bounds__(NT) rescore_queue_kernel(const float* __restrict__ z, Lay L,
+                                                           const float* __restrict__ E,
+                                                           const float* __restrict__ e_sq, int K, int n_cand,
+                                                           const int32_t* __restrict__ q_count,
+                                                           const int32_t* __restrict__ q_rows,
+                                                           const int32_t* __restrict__ q_cand,
+                                                           const uint8_t* __restrict__ q_flags,
+                                                           int64_t* __restrict__ idx,
+                                                           int64_t* __restrict__ fb_rows,
+                                                           int32_t* __restrict__ fb_count, int64_t fb_cap) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * NW;
+  const int total = *q_count;
+  for (int64_t e = (int64_t)blockIdx.x * NW + (threadIdx.x >> 5); e < total; e += nwarps) {
+    const int64_t n = q_rows[e];
+    if (q_flags[e] != 0 && fb_rows) {
+      if (lane == 0) {
+        const int slot = atomicAdd(fb_count, 1);
+        if (slot < fb_cap) {
+          fb_rows[slot] = n;
+          fb_rows[fb_cap + slot] = -1;     // packed (distance, code) key, all ones = +inf
+        }
       }
+      continue;
     }
-    if (incomplete && fb_rows) {
-      int slot = atomicAdd(fb_count, 1);
-      if (slot < fb_cap) {
-        fb_rows[slot] = n;
-        fb_rows[fb_cap + slot] = -1;     // packed (distance, code) key, all ones = +inf
-      }
-    }
-  }
-  __syncthreads();
-  if (!need_tile) return;
-
-  tile_load(z, L, p0, np, tile);
-  __syncthreads();
-  for (int r = warp; r < rows; r += NW) {
-    const int64_t n = n0 + r;
-    const int32_t* cr = cand + n * nc2;
-    const float* sr = score + n * nc2;
-    const float thr = fmaxf(sr[0], sr[n_cand]) - row_margin[n];
-    int live = 0;
-    for (int c = 0; c < nc2; ++c) live += (cr[c] >= 0 && sr[c] >= thr);
-    if (live == 1) continue;                              // done in pass 0
-    const int p = r / L.mult, m = r - p * L.mult;
-    const float* t = tile + p * CP + m * L.D;
+    const int64_t pos = n / L.mult;
+    const int m = (int)(n - pos * L.mult);
+    const float* zr = z + pos_base(L, pos) + (int64_t)m * L.D * L.S;
+    float zv[16];                          // D <= 512 on the tensor-core path
     float zz = 0.f;
-    for (int j = lane; j < L.D; j += 32) zz = fmaf(t[j], t[j], zz);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int j = lane + 32 * i;
+      zv[i] = j < L.D ? __ldg(zr + (int64_t)j * L.S) : 0.f;
+      zz = fmaf(zv[i], zv[i], zz);
+    }
     zz = warp_sum(zz);
     float best_d = INFINITY;
     int best_k = 0x7fffffff;
-    for (int c = 0; c < nc2; ++c) {
-      const int k = cr[c];
-      if (k < 0 || k >= K || !(sr[c] >= thr)) continue;
-      const float* e = E + (size_t)k * L.D;
+    for (int c = 0; c < n_cand; ++c) {
+      const int k = q_cand[e * n_cand + c];
+      if (k < 0 || k >= K) continue;
+      const float* er = E + (size_t)k * L.D;
       float dot = 0.f;
-      for (int j = lane; j < L.D; j += 32) dot = fmaf(t[j], __ldg(e + j), dot);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int j = lane + 32 * i;
+        if (j < L.D) dot = fmaf(zv[i], __ldg(er + j), dot);
+      }
       dot = warp_sum(dot);
       const float d = (zz + __ldg(e_sq + k)) - 2.f * dot;   // quantize.py:45-47 association
       if (d < best_d || (d == best_d && k < best_k)) { best_d = d; best_k = k; }
     }
-    if (lane == 0) idx[n] = (best_k == 0x7fffffff) ? 0 : best_k;
+    if (lane == 0 && best_k != 0x7fffffff) idx[n] = best_k;
   }
 }
 
@@ -520,51 +454,38 @@ __global__ void ema_embed_kernel(float* __restrict__ E, const float* __restrict_
 // =================================================================================================
 using namespace ccvsq;
 
-extern "C" int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf16,
-                                      float* bias, float* e_max, void* stream) {
+extern "C" int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf16, float* e_max,
+                                      void* stream) {
   CCVSQ_REQUIRE(E && e_sq, CCVSQ_NULL_POINTER, "prepare_codebook: E and e_sq must be non-null");
   CCVSQ_REQUIRE(K > 0 && D > 0, CCVSQ_BAD_SHAPE, "prepare_codebook: K=%d D=%d", K, D);
   cudaStream_t st = (cudaStream_t)stream;
-  const int K_pad = (E_bf16 || bias) ? ((K + 255) / 256) * 256 : K;
+  const int K_pad = E_bf16 ? ccvsq_codebook_rows(K) : K;
   if (e_max) CCVSQ_CUDA(cudaMemsetAsync(e_max, 0, sizeof(float), st));
   const int wpb = 8;
-  prepare_codebook_kernel<<<cdiv(K_pad, wpb), wpb * 32, 0, st>>>(
-      E, K, K_pad, D, e_sq, (__nv_bfloat16*)E_bf16, bias, (unsigned int*)e_max);
-  CCVSQ_LAUNCH_CHECK();
-  return CCVSQ_OK;
-}
-
-extern "C" int ccvsq_pack_latents(const float* z, ccvsq_layout lay, void* z_bf16, float* row_margin,
-                                  float margin_scale, const float* e_max, void* stream) {
-  CCVSQ_REQUIRE(z && z_bf16 && row_margin, CCVSQ_NULL_POINTER, "pack_latents: null pointer");
-  Lay L;
-  if (int rc = make_lay(lay, &L)) return rc;
-  const int64_t N_pad = ((L.N + 127) / 128) * 128;
-  const int64_t tiles = (N_pad + (int64_t)PT * L.mult - 1) / ((int64_t)PT * L.mult);
-  const size_t smem = tile_smem_bytes(L);
-  if (int rc = enable_smem(pack_latents_kernel, smem)) return rc;
-  pack_latents_kernel<<<(unsigned)tiles, NT, smem, (cudaStream_t)stream>>>(
-      z, L, (__nv_bfloat16*)z_bf16, row_margin, margin_scale, e_max, N_pad);
+  prepare_codebook_kernel<<<cdiv(K_pad, wpb), wpb * 32, 0, st>>>(E, K, K_pad, D, e_sq, (__nv_bfloat16*)E_bf16,
+                                                                 (unsigned int*)e_max);
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
 }
 
 extern "C" int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, const float* e_sq, int K,
-                             const int32_t* cand_idx, const float* cand_score, const float* row_margin,
-                             int n_cand, const uint8_t* flags, int64_t* idx, int64_t* fallback_ws,
-                             int32_t* fallback_count, int64_t fallback_capacity, void* stream) {
-  CCVSQ_REQUIRE(z && E && e_sq && cand_idx && cand_score && row_margin && idx, CCVSQ_NULL_POINTER,
-                "rescore: null pointer");
+                             int n_cand, const int32_t* queue_count, const int32_t* queue_rows,
+                             const int32_t* queue_cand, const uint8_t* queue_flags, int64_t* idx,
+                             int64_t* fallback_ws, int32_t* fallback_count, int64_t fallback_capacity,
+                             void* stream) {
+  CCVSQ_REQUIRE(z && E && e_sq && queue_count && queue_rows && queue_cand && queue_flags && idx,
+                CCVSQ_NULL_POINTER, "rescore: null pointer");
   CCVSQ_REQUIRE(n_cand >= 1 && n_cand <= CCVSQ_MAX_CAND, CCVSQ_BAD_SHAPE, "rescore: n_cand=%d", n_cand);
   CCVSQ_REQUIRE((fallback_ws == nullptr) == (fallback_count == nullptr), CCVSQ_NULL_POINTER,
                 "rescore: fallback_ws and fallback_count must be given together");
   Lay L;
   if (int rc = make_lay(lay, &L)) return rc;
-  const size_t smem = tile_smem_bytes(L);
-  if (int rc = enable_smem(rescore_kernel, smem)) return rc;
-  rescore_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(
-      z, L, E, e_sq, K, cand_idx, cand_score, row_margin, n_cand, flags, idx, fallback_ws, fallback_count,
-      fallback_capacity);
+  CCVSQ_REQUIRE(L.D <= 512, CCVSQ_UNSUPPORTED, "rescore: D=%d > 512", L.D);
+  int64_t blocks = (L.N + NW - 1) / NW;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  rescore_queue_kernel<<<(unsigned)blocks, NT, 0, (cudaStream_t)stream>>>(
+      z, L, E, e_sq, K, n_cand, queue_count, queue_rows, queue_cand, queue_flags, idx, fallback_ws,
+      fallback_count, fallback_capacity);
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
 }

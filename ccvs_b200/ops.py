@@ -20,9 +20,9 @@ _L = _lib.load()  # fail loudly at import time if the extension is missing
 
 # kernels enqueued by each entry point (ccvsq_prepare_codebook: + one 4-byte memset node)
 _KERNELS_PER_CALL = {
-    "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_pack_latents": 1, "ccvsq_screen": 1,
-    "ccvsq_screen_dump": 1, "ccvsq_screen_trace": 1, "ccvsq_rescore": 1, "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1,
-    "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1, "ccvsq_finalize": 1, "ccvsq_ema_update": 2,
+    "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
+    "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1, "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1,
+    "ccvsq_finalize": 1, "ccvsq_ema_update": 2,
 }
 
 
@@ -123,8 +123,7 @@ class PreparedCodebook:
 
     weight: torch.Tensor          # [K, D] fp32 (the live parameter's storage)
     e_sq: torch.Tensor            # [K] fp32
-    e_bf16: Optional[torch.Tensor]  # [K_pad, D] bf16
-    bias: Optional[torch.Tensor]    # [K_pad] fp32 = -0.5 ||e||^2 (-inf on padding)
+    e_bf16: Optional[torch.Tensor]  # [codebook_rows(K), D + 16] bf16: codes | bias split (hi, mid, lo) | zeros
     e_max: Optional[torch.Tensor]   # [1] fp32 = max ||e||
     version: int
     ptr: int
@@ -142,6 +141,10 @@ def tensor_path_supported(K: int, D: int) -> bool:
     return D % 64 == 0 and 64 <= D <= 512
 
 
+def codebook_rows(K: int) -> int:
+    return int(_L.ccvsq_codebook_rows(int(K)))
+
+
 def prepare_codebook(weight: torch.Tensor, with_bf16: Optional[bool] = None) -> PreparedCodebook:
     w = _req(weight.detach(), torch.float32, "codebook")
     K, D = w.shape
@@ -149,14 +152,12 @@ def prepare_codebook(weight: torch.Tensor, with_bf16: Optional[bool] = None) -> 
         with_bf16 = tensor_path_supported(K, D)
     dev = w.device
     e_sq = torch.empty(K, dtype=torch.float32, device=dev)
-    e_bf16 = bias = e_max = None
+    e_bf16 = e_max = None
     if with_bf16:
-        K_pad = (K + 255) // 256 * 256
-        e_bf16 = torch.empty(K_pad, D, dtype=torch.bfloat16, device=dev)
-        bias = torch.empty(K_pad, dtype=torch.float32, device=dev)
+        e_bf16 = torch.empty(codebook_rows(K), D + 16, dtype=torch.bfloat16, device=dev)
         e_max = torch.empty(1, dtype=torch.float32, device=dev)
-    _call("ccvsq_prepare_codebook", _ptr(w), K, D, _ptr(e_sq), _ptr(e_bf16), _ptr(bias), _ptr(e_max), _stream(dev))
-    return PreparedCodebook(w, e_sq, e_bf16, bias, e_max, weight._version, w.data_ptr())
+    _call("ccvsq_prepare_codebook", _ptr(w), K, D, _ptr(e_sq), _ptr(e_bf16), _ptr(e_max), _stream(dev))
+    return PreparedCodebook(w, e_sq, e_bf16, e_max, weight._version, w.data_ptr())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -171,92 +172,79 @@ def search_exact(z: torch.Tensor, lay: Layout, cb: PreparedCodebook) -> torch.Te
 
 
 @dataclass
-class ScreenResult:
-    cand_idx: torch.Tensor    # [N, 2, n_cand] int32, -1 padded (two epilogue halves, see ccvsq.h)
-    cand_score: torch.Tensor  # [N, 2, n_cand] fp32, slot 0 of each half = that half's maximum
-    flags: torch.Tensor       # [N, 2] uint8, bit0 = more than n_cand codes inside the margin
-    margin: torch.Tensor      # [N_pad] fp32 row margins the screen used
+class ScreenQueue:
+    """Rows the screen could not decide (ccvsq.h): device-side count + per-entry row / candidates / flags."""
 
-    def merged(self):
-        """(idx [N, 2*n_cand] int32 with -1 for dead entries, score, flag [N] bool) after applying
-        the global per-row threshold — what ccvsq_rescore sees (tests / diagnostics)."""
-        N = self.cand_idx.shape[0]
-        sc = self.cand_score.view(N, -1)
-        ci = self.cand_idx.view(N, -1)
-        thr = torch.maximum(self.cand_score[:, 0, 0], self.cand_score[:, 1, 0]) - self.margin[:N]
-        live = (ci >= 0) & (sc >= thr.unsqueeze(1))
-        nc = self.cand_idx.shape[2]
-        f = self.flags.view(N, 2)
-        last_live = live.view(N, 2, nc)[:, :, -1]
-        max_live = self.cand_score[:, :, 0] >= thr.unsqueeze(1)
-        incomplete = (((f & 1) != 0) & last_live) | (((f & 2) != 0) & max_live)
-        return torch.where(live, ci, torch.full_like(ci, -1)), torch.where(live, sc, torch.full_like(sc, float("-inf"))), \
-            incomplete.any(dim=1)
+    count: torch.Tensor   # [1] int32
+    rows: torch.Tensor    # [N] int32
+    cand: torch.Tensor    # [N, n_cand] int32
+    flags: torch.Tensor   # [N] uint8
 
 
-def pack_latents(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, margin_tau: float) -> Tuple[torch.Tensor, torch.Tensor]:
-    N, D = lay.rows, lay.dim
-    N_pad = (N + 127) // 128 * 128
-    zb = torch.empty(N_pad, D, dtype=torch.bfloat16, device=z.device)
-    margin = torch.empty(N_pad, dtype=torch.float32, device=z.device)
-    _call("ccvsq_pack_latents", _ptr(z), lay, _ptr(zb), _ptr(margin), float(margin_tau) * 2.0 ** -8, _ptr(cb.e_max), _stream(z.device))
-    return zb, margin
+def _new_queue(N: int, n_cand: int, dev) -> ScreenQueue:
+    return ScreenQueue(torch.zeros(1, dtype=torch.int32, device=dev), torch.empty(N, dtype=torch.int32, device=dev),
+                       torch.empty(N, n_cand, dtype=torch.int32, device=dev), torch.empty(N, dtype=torch.uint8, device=dev))
 
 
-def screen(zb: torch.Tensor, margin: torch.Tensor, cb: PreparedCodebook, N: int, n_cand: int = 4) -> ScreenResult:
-    dev = zb.device
-    cand_idx = torch.empty(N, 2, n_cand, dtype=torch.int32, device=dev)
-    cand_score = torch.empty(N, 2, n_cand, dtype=torch.float32, device=dev)
-    flags = torch.empty(N, 2, dtype=torch.uint8, device=dev)
-    _call("ccvsq_screen", _ptr(zb), _ptr(margin), _ptr(cb.e_bf16), _ptr(cb.bias), N, cb.K, cb.D, n_cand,
-          _ptr(cand_idx), _ptr(cand_score), _ptr(flags), _stream(dev))
-    return ScreenResult(cand_idx, cand_score, flags, margin)
-
-
-def screen_dump(zb: torch.Tensor, margin: torch.Tensor, cb: PreparedCodebook, N: int, n_cand: int = 4):
-    """Diagnostic: screen + the full fp32 score matrix [N_pad, K_pad] (tests / debugging only)."""
-    dev = zb.device
-    cand_idx = torch.empty(N, 2, n_cand, dtype=torch.int32, device=dev)
-    cand_score = torch.empty(N, 2, n_cand, dtype=torch.float32, device=dev)
-    flags = torch.empty(N, 2, dtype=torch.uint8, device=dev)
-    scores = torch.full((zb.shape[0], cb.e_bf16.shape[0]), float("nan"), dtype=torch.float32, device=dev)
-    _call("ccvsq_screen_dump", _ptr(zb), _ptr(margin), _ptr(cb.e_bf16), _ptr(cb.bias), N, cb.K, cb.D, n_cand,
-          _ptr(cand_idx), _ptr(cand_score), _ptr(flags), _ptr(scores), _stream(dev))
-    return ScreenResult(cand_idx, cand_score, flags, margin), scores
-
-
-def screen_trace(zb: torch.Tensor, margin: torch.Tensor, cb: PreparedCodebook, N: int, n_cand: int = 4):
-    """Diagnostic: per-role event timeline of CTA 0, int64 [4, 4000] (clock64 << 8 | event)."""
-    dev = zb.device
-    cand_idx = torch.empty(N, 2, n_cand, dtype=torch.int32, device=dev)
-    cand_score = torch.empty(N, 2, n_cand, dtype=torch.float32, device=dev)
-    flags = torch.empty(N, 2, dtype=torch.uint8, device=dev)
-    trace = torch.zeros(4, 4000, dtype=torch.int64, device=dev)
-    _call("ccvsq_screen_trace", _ptr(zb), _ptr(margin), _ptr(cb.e_bf16), _ptr(cb.bias), N, cb.K, cb.D, n_cand,
-          _ptr(cand_idx), _ptr(cand_score), _ptr(flags), _ptr(trace), _stream(dev))
-    return trace
-
-
-def rescore(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, sr: ScreenResult, exact_fallback: bool = True,
-            fallback_capacity: int = 1 << 16) -> torch.Tensor:
+def screen(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, margin_tau: float = 1.0):
+    """tcgen05 screening GEMM with fused candidate selection.  Returns (idx int64 [N], ScreenQueue)."""
     dev = z.device
     N = lay.rows
     idx = torch.empty(N, dtype=torch.int64, device=dev)
-    n_cand = sr.cand_idx.shape[2]
+    q = _new_queue(N, n_cand, dev)
+    _call("ccvsq_screen", _ptr(z), lay, _ptr(cb.e_bf16), _ptr(cb.e_max), cb.K, float(margin_tau), n_cand, _ptr(idx),
+          _ptr(q.count), _ptr(q.rows), _ptr(q.cand), _ptr(q.flags), _stream(dev))
+    return idx, q
+
+
+@dataclass
+class ScreenDebug:
+    idx: torch.Tensor         # [N] int64
+    queue: ScreenQueue
+    cand_idx: torch.Tensor    # [N, n_cand] int32, -1 padded, sorted by (score desc, code asc)
+    cand_score: torch.Tensor  # [N, n_cand] fp32, -inf padded
+    flags: torch.Tensor       # [N] uint8
+    margin: torch.Tensor      # [N] fp32
+    scores: Optional[torch.Tensor]   # [N, codebook_rows(K)] fp32
+
+
+def screen_debug(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, margin_tau: float = 1.0,
+                 cta_group: int = 2, dump_scores: bool = False) -> ScreenDebug:
+    """Diagnostic variant: candidate lists / margins for every row, optionally the full score matrix."""
+    dev = z.device
+    N = lay.rows
+    idx = torch.empty(N, dtype=torch.int64, device=dev)
+    q = _new_queue(N, n_cand, dev)
+    cand_idx = torch.empty(N, n_cand, dtype=torch.int32, device=dev)
+    cand_score = torch.empty(N, n_cand, dtype=torch.float32, device=dev)
+    flags = torch.empty(N, dtype=torch.uint8, device=dev)
+    margin = torch.empty(N, dtype=torch.float32, device=dev)
+    scores = torch.full((N, cb.e_bf16.shape[0]), float("nan"), dtype=torch.float32, device=dev) if dump_scores else None
+    _call("ccvsq_screen_debug", _ptr(z), lay, _ptr(cb.e_bf16), _ptr(cb.e_max), cb.K, float(margin_tau), n_cand, cta_group,
+          _ptr(idx), _ptr(q.count), _ptr(q.rows), _ptr(q.cand), _ptr(q.flags), _ptr(cand_idx), _ptr(cand_score), _ptr(flags),
+          _ptr(margin), _ptr(scores), _stream(dev))
+    return ScreenDebug(idx, q, cand_idx, cand_score, flags, margin, scores)
+
+
+def rescore(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, idx: torch.Tensor, q: ScreenQueue,
+            exact_fallback: bool = True, fallback_capacity: int = 1 << 16) -> torch.Tensor:
+    """FP32 re-scoring of the queued rows (in place on idx); flagged rows go to the exact kernel."""
+    dev = z.device
+    N = lay.rows
+    n_cand = q.cand.shape[1]
     fb_rows = fb_count = None
     cap = 0
     if exact_fallback:
         cap = min(N, fallback_capacity)
         fb_rows = torch.empty(2 * cap, dtype=torch.int64, device=dev)     # rows | packed keys
         fb_count = torch.zeros(2, dtype=torch.int32, device=dev)          # queued rows, scratch counter
-    _call("ccvsq_rescore", _ptr(z), lay, _ptr(cb.weight), _ptr(cb.e_sq), cb.K, _ptr(sr.cand_idx),
-          _ptr(sr.cand_score), _ptr(sr.margin), n_cand,
-                         _ptr(sr.flags), _ptr(idx), _ptr(fb_rows), _ptr(fb_count), cap, _stream(dev))
+    _call("ccvsq_rescore", _ptr(z), lay, _ptr(cb.weight), _ptr(cb.e_sq), cb.K, n_cand, _ptr(q.count), _ptr(q.rows),
+          _ptr(q.cand), _ptr(q.flags), _ptr(idx), _ptr(fb_rows), _ptr(fb_count), cap, _stream(dev))
     if exact_fallback:
         # rows with more codes inside the margin than candidate slots: exact FP32 search, count read
         # on the device (no host sync)
         _call("ccvsq_search_exact_rows", _ptr(z), lay, _ptr(cb.weight), _ptr(cb.e_sq), cb.K, _ptr(fb_rows),
-                                       _ptr(fb_count), cap, _ptr(idx), _stream(dev))
+              _ptr(fb_count), cap, _ptr(idx), _stream(dev))
     return idx
 
 
@@ -264,18 +252,17 @@ def search(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, mode: str = "auto
            margin_tau: float = 1.0, exact_fallback: bool = True) -> torch.Tensor:
     """Nearest-code indices, int64 [N].  mode: 'auto' | 'tensor' | 'exact'."""
     _req(z, torch.float32, "z")
+    if mode not in ("auto", "tensor", "exact"):
+        raise ValueError(f"unknown search mode {mode!r}")
     use_tensor = mode == "tensor" or (
         mode == "auto" and cb.e_bf16 is not None and tensor_path_supported(cb.K, cb.D) and lay.rows >= 128 and cb.K >= 64
     )
-    if mode not in ("auto", "tensor", "exact"):
-        raise ValueError(f"unknown search mode {mode!r}")
     if not use_tensor:
         return search_exact(z, lay, cb)
     if cb.e_bf16 is None:
         raise RuntimeError("tensor search needs a codebook prepared with with_bf16=True")
-    zb, margin = pack_latents(z, lay, cb, margin_tau)
-    sr = screen(zb, margin, cb, lay.rows, n_cand)
-    return rescore(z, lay, cb, sr, exact_fallback)
+    idx, q = screen(z, lay, cb, n_cand, margin_tau)
+    return rescore(z, lay, cb, idx, q, exact_fallback)
 
 
 # ------------------------------------------------------------------------------------------------

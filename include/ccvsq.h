@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CCVSQ_VERSION 100 /* major*100 + minor */
+#define CCVSQ_VERSION 101 /* major*100 + minor */
 
 typedef enum ccvsq_status {
   CCVSQ_OK = 0,
@@ -65,12 +65,15 @@ const char* ccvsq_last_error(void); /* thread-local, valid until the next failin
  * builds the BF16 shadow used by the tensor-core screening pass.
  *   E        [K, D]  fp32   codebook (embedding.weight, quantize.py:26)
  *   e_sq     [K]     fp32   out: ||e_k||^2
- *   E_bf16   [K_pad, D] bf16 out (may be NULL): RN-rounded copy, rows K..K_pad-1 zero-filled
- *   bias     [K_pad] fp32   out (may be NULL): -0.5*||e_k||^2, -inf for the padding rows
- *   e_max    [1]     fp32   out (may be NULL): max_k ||e_k||
- * K_pad = K rounded up to a multiple of 256.                                                */
-int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf16, float* bias,
-                           float* e_max, void* stream);
+ *   E_bf16   [ccvsq_codebook_rows(K), D + 16] bf16 out (may be NULL): columns 0..D-1 hold the
+ *            RN-rounded code, columns D..D+2 a 3-term BF16 split (hi, mid, lo) of the bias
+ *            -0.5*||e_k||^2, the rest zero; padding rows are zero with a bias of -3e38.  The screen
+ *            multiplies the 16 extra columns with a constant (1,1,1,0,...) block, so the bias is
+ *            added by the tensor core itself.
+ *   e_max    [1]     fp32   out (may be NULL): max_k ||e_k||                                   */
+int ccvsq_codebook_rows(int K); /* K rounded up to the screen's code tile (96) */
+int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf16, float* e_max,
+                           void* stream);
 
 /* ---- exact FP32 nearest-code search ------------------------------------------------------
  * Replaces quantize.py:45-50 (distance matrix + argmin) without materialising d[N,K].
@@ -80,58 +83,49 @@ int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf
 int ccvsq_search_exact(const float* z, ccvsq_layout lay, const float* E, const float* e_sq, int K,
                        int64_t* idx, void* stream);
 
-/* ---- tensor-core screening: pack, screen, rescore ----------------------------------------
- * ccvsq_pack_latents: rows of z (any layout) -> row-major BF16 [N_pad, D] for the TMA-fed GEMM,
- * plus the per-row screening margin  margin_scale * ||z_n|| * (*e_max)  (fp32; e_max is the device
- * scalar written by ccvsq_prepare_codebook, NULL = 1).  N_pad = N rounded up to 128; padding rows
- * are zero-filled.  With margin_scale = tau * 2^-8 the margin is tau times the first-order bound
- * on the BF16 rounding error of one score for vectors with evenly spread energy.              */
-int ccvsq_pack_latents(const float* z, ccvsq_layout lay, void* z_bf16, float* row_margin,
-                       float margin_scale, const float* e_max, void* stream);
+/* ---- tensor-core screening + FP32 re-scoring ----------------------------------------------
+ * ccvsq_screen: s[n,k] = <bf16(z_n), bf16(e_k)> - 0.5||e_k||^2 on tcgen05 tensor cores (2-CTA MMA,
+ * latents resident in tensor memory, FP32 accumulation) with a fused running candidate selection
+ * per row.  z is the caller's FP32 tensor in any ccvsq_layout (no packing pass).  A code is a
+ * candidate of row n if its score is within
+ *     margin_n = margin_tau * 2^-8 * ||z_n|| * (*e_max)
+ * of the row maximum (tau = 1 is the first-order bound on the BF16 rounding error of one score for
+ * vectors with evenly spread energy; e_max NULL = 1).
+ *   idx         [N] int64 : the only candidate of the row (final), or the best BF16 candidate of a
+ *                           queued row (provisional)
+ *   queue_count [1] int32, zeroed by the caller: rows queued for ccvsq_rescore, i.e. rows with more
+ *                           than one candidate or an incomplete candidate list
+ *   queue_rows  [N] int32 : their row numbers
+ *   queue_cand  [N, n_cand] int32: their candidates sorted by (score desc, code asc), -1 padded
+ *   queue_flags [N] uint8 : bit0 = more than n_cand codes inside the margin (list truncated),
+ *                           bit1 = the kernel's internal list overflowed and dropped a code that may
+ *                           be inside the margin
+ * Requires D % 64 == 0, 64 <= D <= 512, N < 2^31.                                               */
+int ccvsq_screen(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
+                 float margin_tau, int n_cand, int64_t* idx, int32_t* queue_count, int32_t* queue_rows,
+                 int32_t* queue_cand, uint8_t* queue_flags, void* stream);
 
-/* ccvsq_screen: s[n,k] = <bf16(z_n), bf16(e_k)> - 0.5||e_k||^2 on tcgen05 tensor cores with a
- * fused running candidate selection per row.  The kernel's two epilogue groups each own half of
- * the code tiles (even / odd tiles of 256 codes) and report independently, so every per-row output
- * has two halves h = 0, 1:
- *   cand_idx   [N, 2, n_cand] int32: codes whose score is within row_margin[n] of that half's
- *                                    maximum, sorted by (score desc, code asc), -1 padded
- *   cand_score [N, 2, n_cand] fp32 : their BF16-path scores (-inf padded); slot 0 = half maximum
- *   flags      [N, 2] uint8        : bit0 = more than n_cand codes were inside that half's margin
- *                                    (list truncated), bit1 = the half's internal list overflowed
- *                                    and dropped a code that may be inside the margin
- * ccvsq_rescore merges the halves.
- * Requires D % 64 == 0, 64 <= D <= 512.  z_bf16 is [N_pad, D] (N_pad = N rounded up to 128), E_bf16
- * [K_pad, D] and bias [K_pad] (K_pad = K rounded up to 256), row_margin [N_pad].               */
-int ccvsq_screen(const void* z_bf16, const float* row_margin, const void* E_bf16, const float* bias,
-                 int64_t N, int K, int D, int n_cand, int32_t* cand_idx, float* cand_score,
-                 uint8_t* flags, void* stream);
+/* Diagnostic variant (tests only).  Additionally dumps, for EVERY row, the candidate list
+ * cand_idx/cand_score [N, n_cand] (-1 / -inf padded), flags [N], the margin row_margin [N] and, if
+ * `scores` is non-null, the full score matrix [N, ccvsq_codebook_rows(K)] (O(N*K) memory).
+ * cta_group selects the 2-CTA (2, production) or single-CTA (1) MMA path; idx and the queue pointers
+ * may be NULL (together).                                                                       */
+int ccvsq_screen_debug(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
+                       float margin_tau, int n_cand, int cta_group, int64_t* idx, int32_t* queue_count,
+                       int32_t* queue_rows, int32_t* queue_cand, uint8_t* queue_flags, int32_t* cand_idx,
+                       float* cand_score, uint8_t* flags, float* row_margin, float* scores, void* stream);
 
-/* Diagnostic variant: additionally dumps the full score matrix s[N_pad, K_pad] (fp32, row-major,
- * N_pad = N rounded up to 128, K_pad = K rounded up to 256).  Tests only — O(N*K) memory.       */
-int ccvsq_screen_dump(const void* z_bf16, const float* row_margin, const void* E_bf16,
-                      const float* bias, int64_t N, int K, int D, int n_cand, int32_t* cand_idx,
-                      float* cand_score, uint8_t* flags, float* scores, void* stream);
-
-/* Diagnostic variant: CTA 0 records a per-role event timeline into trace (int64 [4][4000], zeroed
- * by the caller; value = clock64 << 8 | event code).  Performance debugging only.               */
-int ccvsq_screen_trace(const void* z_bf16, const float* row_margin, const void* E_bf16,
-                       const float* bias, int64_t N, int K, int D, int n_cand, int32_t* cand_idx,
-                       float* cand_score, uint8_t* flags, long long* trace, void* stream);
-
-/* ccvsq_rescore: merges the two halves of the screen output (a candidate is live if its score is
- * within row_margin[n] of the better half maximum), then re-evaluates the live candidates in FP32
- * with the reference's formula and lowest-index tie-break (quantize.py:45-50); rows with a single
- * live candidate take it directly without touching z.
- * Rows whose candidate set is incomplete w.r.t. the merged threshold (a truncated half whose last
- * slot is still live, or a half that dropped entries while its maximum is live) are queued for the
- * exact fallback:
+/* ccvsq_rescore: re-evaluates the candidates of the queued rows in FP32 with the reference's
+ * formula and lowest-index tie-break (quantize.py:45-50) and overwrites idx[row].  The queue length
+ * is read on the device (no host sync).  Rows with queue_flags != 0 are passed on to the exact
+ * fallback:
  *   fallback_ws    int64 [2*fallback_capacity]: row numbers, then packed (distance, code) keys
  *   fallback_count int32 [2], zeroed by the caller: [0] rows queued, [1] scratch counter
- * (both may be NULL to ignore overflow rows).                                                   */
-int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, const float* e_sq, int K,
-                  const int32_t* cand_idx, const float* cand_score, const float* row_margin,
-                  int n_cand, const uint8_t* flags, int64_t* idx, int64_t* fallback_ws,
-                  int32_t* fallback_count, int64_t fallback_capacity, void* stream);
+ * (both may be NULL: such rows are then resolved among their listed candidates).                */
+int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, const float* e_sq, int K, int n_cand,
+                  const int32_t* queue_count, const int32_t* queue_rows, const int32_t* queue_cand,
+                  const uint8_t* queue_flags, int64_t* idx, int64_t* fallback_ws, int32_t* fallback_count,
+                  int64_t fallback_capacity, void* stream);
 
 /* Exact FP32 search restricted to the rows queued by ccvsq_rescore (count read on the device, no
  * host sync).  The codebook is split across CTAs, partial minima meet through 64-bit atomicMin on

@@ -29,24 +29,26 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_version():
-    assert _lib.load().ccvsq_version() == 100
+    assert _lib.load().ccvsq_version() == 101
 
 
 def test_argument_validation_without_gpu():
     lib = _lib.load()
     null = ctypes.c_void_p(0)
     one = ctypes.c_void_p(16)
-    assert lib.ccvsq_prepare_codebook(null, 4, 4, null, null, null, null, null) == -5    # NULL_POINTER
+    assert lib.ccvsq_prepare_codebook(null, 4, 4, null, null, null, null) == -5    # NULL_POINTER
     assert b"non-null" in lib.ccvsq_last_error()
-    assert lib.ccvsq_prepare_codebook(one, 0, 4, one, null, null, null, null) == -1       # BAD_SHAPE
+    assert lib.ccvsq_prepare_codebook(one, 0, 4, one, null, null, null) == -1       # BAD_SHAPE
     bad = _lib.Layout(4, 6, 4, 4)      # C not divisible by mult
     assert lib.ccvsq_search_exact(one, bad, one, one, 8, one, null) == -1
-    ok = _lib.Layout(4, 100, 4, 1)     # D = 100: not a tensor-core shape
-    assert lib.ccvsq_screen(one, one, one, one, 128, 256, 100, 4, one, one, one, null) == -2   # UNSUPPORTED
-    assert lib.ccvsq_screen(one, one, one, one, 128, 256, 128, 9, one, one, one, null) == -1   # n_cand > 8
-    assert lib.ccvsq_screen(ctypes.c_void_p(8), one, one, one, 128, 256, 128, 4, one, one, one, null) == -3  # MISALIGNED
+    odd = _lib.Layout(4, 100, 4, 1)    # D = 100: not a tensor-core shape
+    good = _lib.Layout(4, 128, 4, 1)
+    assert lib.ccvsq_screen(one, odd, one, one, 256, 1.0, 4, one, one, one, one, one, null) == -2    # UNSUPPORTED
+    assert lib.ccvsq_screen(one, good, one, one, 256, 1.0, 9, one, one, one, one, one, null) == -1   # n_cand > 8
+    assert lib.ccvsq_screen(ctypes.c_void_p(8), good, one, one, 256, 1.0, 4, one, one, one, one, one, null) == -3  # MISALIGNED
+    assert lib.ccvsq_screen(one, good, one, one, 256, 1.0, 4, null, one, one, one, one, null) == -5  # NULL_POINTER
+    assert lib.ccvsq_codebook_rows(1024) == 1056 and lib.ccvsq_codebook_rows(96) == 96
     assert lib.ccvsq_finalize(null, null, null, null, 4, 4, 0.0, 1.0, 0.25, null, null, null, null) == -1
-    del ok
 
 
 def test_layout_struct_matches_header():

@@ -114,49 +114,62 @@ def test_search_vs_oracle(shape, K, D, dist, mode):
     torch.testing.assert_close(pcb.e_sq.cpu(), (cb ** 2).sum(1), rtol=1e-6, atol=0)
 
 
-def test_screen_scores_and_candidates():
-    """The tcgen05 GEMM itself: candidate scores equal <bf16(z), bf16(e)> - 0.5|e|^2 (FP32 accumulate)
-    and every code inside the margin is reported."""
-    shape, K, D = (8, 256, 8, 8), 1024, 256
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("shape,K,D", [((8, 256, 8, 8), 1024, 256), ((5, 128, 7, 9), 300, 128), ((200, 512), 200, 512),
+                                       ((3, 64, 16, 16), 96, 64)])
+def test_screen_scores_and_candidates(shape, K, D, cta_group):
+    """The tcgen05 GEMM itself: scores equal <bf16(z), bf16(e)> - 0.5|e|^2 (FP32 accumulate; the bias
+    enters through the K-extension of the codebook shadow) and every code inside the margin is reported."""
     z, cb = vq_oracle.synth(shape, K, D, "T", seed=7)
     z = torch.randn_like(z)        # unit-variance latents against an N(0,1) codebook: real competition
     lay = ops.layout_of(shape, D, 1)
     pcb = ops.prepare_codebook(cb.to(DEV))
-    zb, margin = ops.pack_latents(z.to(DEV), lay, pcb, margin_tau=4.0)
-    sr = ops.screen(zb, margin, pcb, lay.rows, n_cand=8)
     N = lay.rows
     rows = vq_oracle.to_channel_last(z).reshape(-1, D).to(DEV)
-    assert torch.equal(zb[:N].float(), rows.to(torch.bfloat16).float())
-    torch.testing.assert_close(margin[:N], 4.0 * 2.0 ** -8 * rows.norm(dim=1) * cb.norm(dim=1).max().to(DEV), rtol=1e-5, atol=0)
-    s = zb[:N].float() @ pcb.e_bf16[:K].float().t() + pcb.bias[:K]
-    top = s.max(dim=1)
-    ci, sc, flag = sr.merged()                  # both epilogue halves under the global row threshold
-    best = sc.max(dim=1)
+    # codebook shadow: rounded codes + a bias split that reproduces -0.5|e|^2 to FP32 accuracy
+    assert pcb.e_bf16.shape == (ops.codebook_rows(K), D + 16)
+    assert torch.equal(pcb.e_bf16[:K, :D].float(), cb.to(DEV).to(torch.bfloat16).float())
+    bias = pcb.e_bf16[:K, D:].float().sum(1)
+    torch.testing.assert_close(bias, -0.5 * (cb.to(DEV) ** 2).sum(1), rtol=1e-6, atol=0)
+    assert bool((pcb.e_bf16[K:, D] < -1e38).all()) and bool((pcb.e_bf16[K:, :D] == 0).all())
+
+    sd = ops.screen_debug(z.to(DEV), lay, pcb, n_cand=8, margin_tau=4.0, cta_group=cta_group, dump_scores=True)
+    torch.testing.assert_close(sd.margin, 4.0 * 2.0 ** -8 * rows.norm(dim=1) * cb.norm(dim=1).max().to(DEV), rtol=1e-5, atol=0)
+    s = rows.to(torch.bfloat16).float() @ pcb.e_bf16[:K, :D].float().t() + bias
     # FP32 accumulation order differs between the tensor core and torch.matmul: |s| ~ 1e2 -> 2e-2
-    torch.testing.assert_close(best.values, top.values, rtol=1e-4, atol=2e-2)
-    # the best candidate is an argmax up to accumulation-order noise
-    best_code = ci.gather(1, best.indices.unsqueeze(1)).squeeze(1).long()
-    picked = s.gather(1, best_code.unsqueeze(1)).squeeze(1)
-    assert bool((top.values - picked <= 2e-2).all())
-    # reported scores are the scores of the reported codes
+    torch.testing.assert_close(sd.scores[:, :K], s, rtol=1e-4, atol=2e-2)
+    assert bool((sd.scores[:, K:] < -1e38).all())
+    top = s.max(dim=1)
+    ci, sc = sd.cand_idx, sd.cand_score
+    torch.testing.assert_close(sc[:, 0], top.values, rtol=1e-4, atol=2e-2)
+    picked = s.gather(1, ci[:, :1].long()).squeeze(1)
+    assert bool((top.values - picked <= 2e-2).all())          # slot 0 is an argmax up to accumulation noise
+    assert torch.equal(sd.idx, ci[:, 0].long())
     live = ci >= 0
     rep = s.gather(1, ci.clamp_min(0).long())
-    assert bool(((rep - sc).abs()[live] <= 2e-2).all())
+    assert bool(((rep - sc).abs()[live] <= 2e-2).all())       # reported scores belong to the reported codes
     # completeness: codes clearly inside the margin must be listed (unless the row overflowed)
-    inside = s >= (top.values - margin[:N] + 5e-2).unsqueeze(1)
-    ok_rows = ~flag
+    inside = s >= (top.values - sd.margin + 5e-2).unsqueeze(1)
+    ok_rows = sd.flags == 0
     assert float(ok_rows.float().mean()) > 0.5
     listed = torch.zeros(N, K + 1, dtype=torch.bool, device=DEV)
     listed.scatter_(1, torch.where(live, ci, torch.full_like(ci, K)).long(), True)
     listed = listed[:, :K]
     assert bool((listed[ok_rows] | ~inside[ok_rows]).all())
-    assert float((live.sum(1) > 1).float().mean()) > 0.05      # the margin really admits rivals here
-    # each half is sorted by score descending
-    hs = sr.cand_score
-    assert bool((hs[:, :, :-1] >= hs[:, :, 1:]).all())
-    # no duplicates among live candidates
+    # nothing clearly outside the margin is listed
+    outside = s < (top.values - sd.margin - 5e-2).unsqueeze(1)
+    assert not bool((listed & outside).any())
+    if K >= 300:
+        assert float((live.sum(1) > 1).float().mean()) > 0.05     # the margin really admits rivals here
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all())              # sorted by score descending
     srt = torch.where(live, ci, torch.arange(-1, -1 - ci.shape[1], -1, device=DEV).expand_as(ci)).sort(dim=1).values
-    assert bool((srt[:, 1:] != srt[:, :-1]).all())
+    assert bool((srt[:, 1:] != srt[:, :-1]).all())            # no duplicates among live candidates
+    # the queue holds exactly the rows with more than one candidate or a flag
+    nq = int(sd.queue.count)
+    expect = ((live.sum(1) > 1) | (sd.flags != 0)).nonzero().squeeze(1)
+    assert torch.equal(sd.queue.rows[:nq].long().sort().values, expect)
+    order = sd.queue.rows[:nq].long()
+    assert torch.equal(sd.queue.cand[:nq], ci[order]) and torch.equal(sd.queue.flags[:nq], sd.flags[order])
 
 
 def test_overflow_rows_fall_back_to_exact():
@@ -173,9 +186,8 @@ def test_overflow_rows_fall_back_to_exact():
     idx = ops.search(z.to(DEV), lay, pcb, mode="tensor", n_cand=4).cpu()
     expect = torch.tensor([100, 7, 100, 100]).repeat(64)
     assert torch.equal(idx, expect)
-    zb, margin = ops.pack_latents(z.to(DEV), lay, pcb, 1.0)
-    sr = ops.screen(zb, margin, pcb, 256, 4)
-    flag = sr.merged()[2].cpu().view(64, 4)
+    sd = ops.screen_debug(z.to(DEV), lay, pcb, n_cand=4, margin_tau=1.0)
+    flag = (sd.flags != 0).cpu().view(64, 4)
     assert bool(flag[:, [0, 2, 3]].all()) and not bool(flag[:, 1].any())
 
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU visit: parity tests, benches, ncu launch list and a full capture of the screen kernel.
+# One GPU visit: parity tests, benches, ncu launch list and full captures of the screen kernel.
 # Usage (from the repo root, on the GPU box): bash tools/gpu_round.sh [tag]
 TAG=${1:-r01}
 OUT=gpurun_out/$TAG
