@@ -61,9 +61,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on a barrier given by a shared::cluster address (own or peer CTA)
+// arrive on a barrier given by a shared::cluster address (own or peer CTA).  Default (CTA-scope
+// release) semantics on purpose: what the waiter consumes is tensor-memory state ordered by
+// tcgen05.fence, and a cluster-scope release costs a GPU-wide MEMBAR (~800 cycles) per arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
@@ -90,6 +92,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();   // ~2 s
+  }
+}
+// Long waits (a whole code sweep): back off so the spin does not take issue slots from working warps.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(256);
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {
@@ -120,23 +131,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
   }
 }
-// D[tmem] (+)= A[tmem] * B[smem]^T, BF16 x BF16 -> FP32
+// D[tmem] (+)= A[tmem] * B[smem]^T, BF16 x BF16 -> FP32.  The shared-memory descriptor is passed as
+// two 32-bit halves so that advancing it is a single 32-bit add on the (warp-uniform) low word.
 template <int CG>
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t b_desc_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
   if constexpr (CG == 1) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
   } else {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 // Arrive on `bar` (same offset in every CTA of the group) once all previously issued MMAs retire.
 template <int CG>
@@ -203,25 +221,15 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 format, version 1):
-// 8-row x 128-byte swizzle atoms, stride between 8-row groups (SBO) = 1024 B, LBO unused.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address  [0,14)
-  d |= (uint64_t)(1024 >> 4) << 32;                  // SBO            [32,46)
-  d |= (uint64_t)1 << 46;                            // version = 1    [46,48)
-  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B   [61,64)
-  return d;
-}
+// Shared-memory matrix descriptors (sm_100 format, version 1), split in 32-bit halves.
+// K-major, 128B swizzle: 8-row x 128-byte atoms, SBO (8-row group stride) = 1024 B, LBO unused.
+//   lo = start address >> 4 [0,14) | LBO >> 4 [16,30);  hi = SBO >> 4 [0,14) | version [14,16) | layout [29,32)
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 // K-major, no swizzle: 8-row x 16-byte core matrices; SBO = 128 B between 8-row groups, LBO = byte
 // distance between the two 16-byte K chunks of one 16-element K step.
-__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // LBO            [16,30)
-  d |= (uint64_t)(128 >> 4) << 32;                   // SBO
-  d |= (uint64_t)1 << 46;
-  return d;
+constexpr uint32_t DESC_HI_NOSW = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes = 0) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
 // kind::f16 instruction descriptor: FP32 accum, BF16 x BF16, both K-major, M x N.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
@@ -414,27 +422,31 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
 
   if (warp == 0) {
     // =========================== TMA producer (every CTA: its half of each B tile) ===============
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int gt = group; gt < num_group_tiles; gt += num_groups) {
-        for (int j = 0; j < n_tiles; ++j) {
-          mbar_wait(empty_bar(slot), phase ^ 1);
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers);
+    // one elected lane issues.
+    int slot = 0;
+    uint32_t phase = 0;
+    const uint32_t fb0 = (CG == 1) ? full_bar(0) : mapa(full_bar(0), 0);
+    for (int gt = group; gt < num_group_tiles; gt += num_groups) {
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(empty_bar(slot), phase ^ 1);
+        if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(full_bar(slot), lay.slot_tx * CG);
-          const uint32_t fb = (CG == 1) ? full_bar(slot) : mapa(full_bar(slot), 0);
+          const uint32_t fb = fb0 + 8u * slot;
           const uint32_t dst = smem_base + lay.slots + (uint32_t)slot * lay.slot_bytes;
           const int row0 = j * BN + (int)rank * ROWS;
           for (int kb = 0; kb < dblk; ++kb)
             tma_load_2d<CG>(dst + kb * lay.block_bytes, &map_b, fb, kb * 64, row0);
           tma_load_2d<CG>(dst + lay.ext_off, &map_ext, fb, dblk * 64, row0);
           tma_load_2d<CG>(dst + lay.ext_off + ROWS * 16, &map_ext, fb, dblk * 64 + 8, row0);
-          if (++slot == nslots) { slot = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++slot == nslots) { slot = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA) ===========================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
       int slot = 0;
       uint32_t phase = 0, acc_it = 0, tl = 0;
@@ -447,19 +459,25 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           if (j == 0) mbar_wait(a_full(ab), a_phase);
           mbar_wait(full_bar(slot), phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + TM_ACC + b * BN;
-          const uint32_t sbase = smem_base + lay.slots + (uint32_t)slot * lay.slot_bytes;
-          // bias first (overwrites the accumulator), then the D/16 K steps of the dot product
-          umma_ts<CG>(d_tmem, tmem_base + TM_EXT, make_nosw_desc(sbase + lay.ext_off, ROWS * 16), idesc, 0u);
-          for (int kb = 0; kb < dblk; ++kb) {
-            const uint32_t b_addr = sbase + kb * lay.block_bytes;
+          if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + TM_ACC + b * BN;
+            const uint32_t sbase = smem_base + lay.slots + (uint32_t)slot * lay.slot_bytes;
+            // bias first (overwrites the accumulator), then the D/16 K steps of the dot product
+            umma_ts<CG>(d_tmem, tmem_base + TM_EXT, desc_lo(sbase + lay.ext_off, ROWS * 16), DESC_HI_NOSW, idesc, 0u);
+            uint32_t lo = desc_lo(sbase);
+            uint32_t a_addr = a_tmem;
+            for (int kb = 0; kb < dblk; ++kb) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ts<CG>(d_tmem, a_tmem + kb * 32 + k * 8, make_sw128_desc(b_addr + k * 32), idesc, 1u);
+              for (int k = 0; k < 4; ++k)
+                umma_ts<CG>(d_tmem, a_addr + k * 8, lo + k * 2, DESC_HI_SW128, idesc, 1u);
+              lo += lay.block_bytes >> 4;
+              a_addr += 32;
+            }
+            umma_commit<CG>(empty_bar(slot));      // B slot reusable once these MMAs retire
+            umma_commit<CG>(tmem_full(b));         // accumulator tile complete
+            if (j == n_tiles - 1) umma_commit<CG>(a_empty(ab));   // last reader of this A buffer
           }
-          umma_commit<CG>(empty_bar(slot));      // B slot reusable once these MMAs retire
-          umma_commit<CG>(tmem_full(b));         // accumulator tile complete
-          if (j == n_tiles - 1) umma_commit<CG>(a_empty(ab));   // last reader of this A buffer
+          __syncwarp();
           if (++slot == nslots) { slot = 0; phase ^= 1; }
         }
       }
@@ -485,7 +503,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       }
       float va[32], vb[32];
       load_chunk(va, p, L.S, valid);            // in flight while waiting for the buffer
-      mbar_wait(a_empty(ab), a_phase ^ 1);
+      mbar_wait_sleep(a_empty(ab), a_phase ^ 1);
       tc_fence_after();
       float ss = 0.f;
       const uint32_t dst = lane_base + ab * a_cols;
@@ -516,7 +534,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         }
       }
       tmem_st_wait();
-      mbar_wait(norm_empty(ab), a_phase ^ 1);   // the epilogue has read the previous norms of this buffer
+      mbar_wait_sleep(norm_empty(ab), a_phase ^ 1);   // the epilogue has read the previous norms of this buffer
       norm_s[(ab * 2 + h) * BM + r] = ss;
       tc_fence_before();
       __syncwarp();
