@@ -248,10 +248,9 @@ constexpr uint32_t LIST_BYTES = LCAP * (SC_STRIDE + CO_STRIDE);
 constexpr int SCREEN_THREADS = 512;
 constexpr int MAX_SLOTS = 8;
 // tensor-memory columns (32-bit): two accumulators, the constant bias-extension A block, A buffers
-constexpr uint32_t TM_ACC = 0;
-constexpr uint32_t TM_EXT = 2 * BN;
-constexpr uint32_t TM_A = 2 * BN + 8;
+//   [0, nacc*BN) accumulators | [nacc*BN, +8) bias-extension A block | then abuf_n A buffers of D/2
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int MAX_ACC = 4;
 
 struct ScreenSmem {
   uint32_t slots, list, norm, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
@@ -338,6 +337,82 @@ struct ScreenOut {
   float* dbg_scores;       // [N, K_pad]
 };
 
+// Candidates of one row once all codes have been seen: every listed code with score >= runmax -
+// margin, sorted by (score desc, code asc), at most n_cand of them.  The list is in increasing code
+// order, so a strict '>' scan keeps the lowest code among equal scores.  Rows with exactly one
+// candidate are final; the others are queued for FP32 re-scoring.  Kept out of line (and rolled) so
+// the per-tile loop stays small in the instruction cache.
+__device__ __noinline__ void finalize_row(uint32_t sc_base, uint32_t co_base, uint32_t pco, float runmax,
+                                          float margin, float dropped_max, int n_cand, int64_t row,
+                                          const ScreenOut& out) {
+  const float thr = runmax - margin;
+  const uint32_t n = (pco - co_base) / CO_STRIDE;
+  uint32_t within = 0;
+  float best_s = -INFINITY;
+  int best_i = -1;
+#pragma unroll 1
+  for (uint32_t e = 0; e < n; ++e) {
+    float sc[4];
+    uint32_t code;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {      // branch-free (padding codes carry -3e38 and never pass)
+      within += (sc[u] >= thr) ? 1u : 0u;
+      const bool better = sc[u] > best_s;
+      best_s = better ? sc[u] : best_s;
+      best_i = better ? (int)code + u : best_i;
+    }
+  }
+  const uint8_t flag = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped_max >= thr ? 2 : 0));
+  const bool final_row = within == 1 && flag == 0;
+  if (out.idx) out.idx[row] = best_i;
+  if (final_row && !out.dbg_cand) return;
+
+  int slot = -1;
+  if (!final_row && out.q_count) {
+    slot = atomicAdd(out.q_count, 1);
+    out.q_rows[slot] = (int32_t)row;
+    out.q_flags[slot] = flag;
+  }
+  if (out.dbg_cand) {
+    out.dbg_flags[row] = flag;
+    out.dbg_margin[row] = margin;
+  }
+  float prev_s = INFINITY;
+  int prev_i = -1;
+#pragma unroll 1
+  for (int c = 0; c < n_cand; ++c) {   // repeated selection: next (score desc, code asc) after (prev_s, prev_i)
+    float bs_ = -INFINITY;
+    int bi = 0x7fffffff;
+    if (prev_i != 0x7fffffff) {
+#pragma unroll 1
+      for (uint32_t e = 0; e < n; ++e) {
+        float sc[4];
+        uint32_t code;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = (int)code + u;
+          const float x = sc[u];
+          const bool after_prev = (x < prev_s) || (x == prev_s && i > prev_i);
+          const bool better = (x > bs_) || (x == bs_ && i < bi);
+          if (x >= thr && after_prev && better) { bs_ = x; bi = i; }
+        }
+      }
+    }
+    prev_s = bs_;
+    prev_i = bi;
+    const int code_out = bi == 0x7fffffff ? -1 : bi;
+    if (slot >= 0) out.q_cand[(int64_t)slot * n_cand + c] = code_out;
+    if (out.dbg_cand) {
+      out.dbg_cand[row * n_cand + c] = code_out;
+      out.dbg_score[row * n_cand + c] = bs_;
+    }
+  }
+}
+
 // 32 consecutive dims of one latent row -> registers (S == 1: contiguous row, else stride S)
 __device__ __forceinline__ void load_chunk(float (&v)[32], const float* __restrict__ p, int64_t S, bool valid) {
   if (!valid) {
@@ -362,15 +437,17 @@ template <int CG>
 __global__ void __launch_bounds__(SCREEN_THREADS, 1)
 screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_ext,
               const float* __restrict__ z, const Lay L, const float* __restrict__ e_max, float margin_scale,
-              int K_pad, int n_tiles, int dblk, int n_cand, int num_group_tiles, const ScreenOut out) {
+              int K_pad, int n_tiles, int dblk, int nacc, int abuf_n, int n_cand, int num_group_tiles,
+              const ScreenOut out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ScreenSmem lay = screen_smem_layout(dblk, CG);
   const uint32_t smem_base = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 1) ? 0u : cluster_ctarank();
   const int group = (int)blockIdx.x / CG, num_groups = (int)gridDim.x / CG;
   const int nslots = lay.nslots;
-  const int abuf_n = dblk <= 4 ? 2 : 1;             // A buffers in tensor memory
+  const uint32_t TM_EXT = (uint32_t)nacc * BN, TM_A = TM_EXT + 8;   // tensor-memory column map
   const uint32_t a_cols = (uint32_t)dblk * 32;      // 32-bit columns per A buffer (D/2)
   constexpr int ROWS = BN / CG;                     // codes of a tile in this CTA's shared memory
 
@@ -379,12 +456,12 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_SLOTS + s); };
   auto tmem_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + b); };
-  auto tmem_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 2 + b); };
-  auto a_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 4 + b); };
-  auto a_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 6 + b); };
-  auto norm_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 8 + b); };
-  auto norm_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 10 + b); };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + lay.bars + 8u * (2 * MAX_SLOTS + 12));
+  auto tmem_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + MAX_ACC + b); };
+  auto a_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 2 * MAX_ACC + b); };
+  auto a_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 2 * MAX_ACC + 2 + b); };
+  auto norm_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 2 * MAX_ACC + 4 + b); };
+  auto norm_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 2 * MAX_ACC + 6 + b); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + lay.bars + 8u * (2 * MAX_SLOTS + 2 * MAX_ACC + 8));
   float* norm_s = reinterpret_cast<float*>(smem + lay.norm);
 
   if ((smem_base & 1023u) != 0) __trap();   // SWIZZLE_128B needs 1024-byte aligned tiles
@@ -395,9 +472,11 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < MAX_ACC; ++b) {
       mbar_init(tmem_full(b), 1);
       mbar_init(tmem_empty(b), 4 * CG);     // one arrive per epilogue warp of every CTA in the group
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(a_full(b), 8 * CG);         // one arrive per loader warp of every CTA in the group
       mbar_init(a_empty(b), 1);
       mbar_init(norm_full(b), 8);
@@ -449,18 +528,17 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
       int slot = 0;
-      uint32_t phase = 0, acc_it = 0, tl = 0;
+      uint32_t phase = 0, tl = 0, b = 0, b_phase = 0;
       for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
         const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
         const uint32_t a_tmem = tmem_base + TM_A + ab * a_cols;
-        for (int j = 0; j < n_tiles; ++j, ++acc_it) {
-          const uint32_t b = acc_it & 1;
-          mbar_wait(tmem_empty(b), ((acc_it >> 1) & 1) ^ 1);
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(tmem_empty(b), b_phase ^ 1);
           if (j == 0) mbar_wait(a_full(ab), a_phase);
           mbar_wait(full_bar(slot), phase);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t d_tmem = tmem_base + TM_ACC + b * BN;
+            const uint32_t d_tmem = tmem_base + b * BN;
             const uint32_t sbase = smem_base + lay.slots + (uint32_t)slot * lay.slot_bytes;
             // bias first (overwrites the accumulator), then the D/16 K steps of the dot product
             umma_ts<CG>(d_tmem, tmem_base + TM_EXT, desc_lo(sbase + lay.ext_off, ROWS * 16), DESC_HI_NOSW, idesc, 0u);
@@ -479,6 +557,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           }
           __syncwarp();
           if (++slot == nslots) { slot = 0; phase ^= 1; }
+          if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
         }
       }
     }
@@ -552,7 +631,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     const uint32_t co_limit = co_base + (LCAP - 2) * CO_STRIDE;   // appending 2 groups needs pco <= co_limit
     const uint32_t te_bar = (CG == 1) ? tmem_empty(0) : mapa(tmem_empty(0), 0);
     const float emax = e_max ? __ldg(e_max) : 1.f;
-    uint32_t acc_it = 0, tl = 0;
+    uint32_t tl = 0, b = 0, b_phase = 0;
 
     for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
       const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
@@ -565,11 +644,10 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       float dropped_max = -FLT_MAX;
       uint32_t psc = sc_base, pco = co_base;    // next free list entry
 
-      for (int j = 0; j < n_tiles; ++j, ++acc_it) {
-        const uint32_t b = acc_it & 1;
-        mbar_wait(tmem_full(b), (acc_it >> 1) & 1);
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(tmem_full(b), b_phase);
         tc_fence_after();
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + b * BN;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
         const int col0 = j * BN;
 
         // One 32-column chunk of this thread's row.  Fast path: a max tree (FMNMX3).  A chunk can
@@ -634,86 +712,10 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
         }
         process(ra, 64);
+        if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
       }
 
-      // ---- candidates of the row: every listed code with score >= runmax - margin, sorted by
-      //      (score desc, code asc), at most n_cand of them.  The list is in increasing code order,
-      //      so a strict '>' scan keeps the lowest code among equal scores.
-      if (row < L.N) {
-        const float thr = runmax - margin;
-        const uint32_t n = (pco - co_base) / CO_STRIDE;
-        uint32_t within = 0;
-        float best_s = -INFINITY;
-        int best_i = -1;
-        for (uint32_t e = 0; e < n; ++e) {
-          float sc[4];
-          uint32_t code;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {      // branch-free (padding codes carry -3e38 and never pass)
-            within += (sc[u] >= thr) ? 1u : 0u;
-            const bool better = sc[u] > best_s;
-            best_s = better ? sc[u] : best_s;
-            best_i = better ? (int)code + u : best_i;
-          }
-        }
-        const uint8_t flag = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped_max >= thr ? 2 : 0));
-        const bool final_row = within == 1 && flag == 0;
-        const bool want_list = !final_row || out.dbg_cand;
-        int cand[CCVSQ_MAX_CAND];
-        float cscore[CCVSQ_MAX_CAND];
-#pragma unroll
-        for (int c = 0; c < CCVSQ_MAX_CAND; ++c) { cand[c] = -1; cscore[c] = -INFINITY; }
-        cand[0] = best_i;
-        cscore[0] = best_s;
-        if (want_list && within > 1) {      // near-ties: repeated selection
-          float prev_s = best_s;
-          int prev_i = best_i;
-#pragma unroll
-          for (int c = 1; c < CCVSQ_MAX_CAND; ++c) {
-            if (c >= n_cand || prev_i == 0x7fffffff) continue;
-            float bs_ = -INFINITY;
-            int bi = 0x7fffffff;
-            for (uint32_t e = 0; e < n; ++e) {
-              float sc[4];
-              uint32_t code;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int i = (int)code + u;
-                const float x = sc[u];
-                const bool after_prev = (x < prev_s) || (x == prev_s && i > prev_i);
-                const bool better = (x > bs_) || (x == bs_ && i < bi);
-                if (x >= thr && after_prev && better) { bs_ = x; bi = i; }
-              }
-            }
-            prev_s = bs_;
-            prev_i = bi;
-            if (bi != 0x7fffffff) { cand[c] = bi; cscore[c] = bs_; }
-          }
-        }
-        if (out.idx) out.idx[row] = best_i;
-        if (!final_row && out.q_count) {
-          const int slot = atomicAdd(out.q_count, 1);
-          out.q_rows[slot] = (int32_t)row;
-          out.q_flags[slot] = flag;
-#pragma unroll
-          for (int c = 0; c < CCVSQ_MAX_CAND; ++c)
-            if (c < n_cand) out.q_cand[(int64_t)slot * n_cand + c] = cand[c];
-        }
-        if (out.dbg_cand) {
-#pragma unroll
-          for (int c = 0; c < CCVSQ_MAX_CAND; ++c)
-            if (c < n_cand) {
-              out.dbg_cand[row * n_cand + c] = cand[c];
-              out.dbg_score[row * n_cand + c] = cscore[c];
-            }
-          out.dbg_flags[row] = flag;
-          out.dbg_margin[row] = margin;
-        }
-      }
+      if (row < L.N) finalize_row(sc_base, co_base, pco, runmax, margin, dropped_max, n_cand, row, out);
     }
   }
 
@@ -794,8 +796,19 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CCVSQ_CUDA(cudaLaunchKernelEx(&cfg, kern, mb, mx, z, L, e_max, margin_scale, K_pad, K_pad / BN, dblk, n_cand,
-                                (int)group_tiles, out));
+  // Tensor-memory budget (512 columns): nacc accumulators of BN, 8 columns of bias extension, abuf A
+  // buffers of D/2.  Long code sweeps prefer a third accumulator (the MMA -> epilogue -> MMA chain
+  // per accumulator is longer than two tile times) over a second A buffer (one bubble per sweep);
+  // short sweeps prefer streaming the next A tile under the MMAs.
+  const int n_tiles = K_pad / BN;
+  const int a_cols = D / 2;
+  int abuf = (2 * a_cols + 8 + 2 * BN <= (int)TMEM_COLS) ? 2 : 1;
+  if (abuf == 2 && n_tiles >= 24 && (2 * a_cols + 8 + 3 * BN > (int)TMEM_COLS)) abuf = 1;
+  int nacc = ((int)TMEM_COLS - 8 - abuf * a_cols) / BN;
+  if (nacc > 3) nacc = 3;
+  CCVSQ_REQUIRE(nacc >= 2, CCVSQ_UNSUPPORTED, "screen: D=%d leaves %d accumulators", D, nacc);
+  CCVSQ_CUDA(cudaLaunchKernelEx(&cfg, kern, mb, mx, z, L, e_max, margin_scale, K_pad, n_tiles, dblk, nacc, abuf,
+                                n_cand, (int)group_tiles, out));
   return CCVSQ_OK;
 }
 
