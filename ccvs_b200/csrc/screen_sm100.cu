@@ -241,7 +241,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // ------------------------------------------------------------------------------------------------
 constexpr int BM = 128;              // latent rows per CTA (TMEM lanes)
 constexpr int BN = SCREEN_BN;        // codes per accumulator tile (UMMA N)
-constexpr int LCAP = 8;              // candidate-list entries (groups of 4 codes) per row
+constexpr int LCAP = 16;             // candidate-list entries (groups of 4 codes) per row
+constexpr int LKEEP = LCAP - 8;      // one slow path appends up to 8 groups: compact down to this many first
 constexpr uint32_t SC_STRIDE = BM * 16;   // entry e of a row: 4 raw scores at sc_base + e*SC_STRIDE ...
 constexpr uint32_t CO_STRIDE = BM * 4;    // ... and the first code of the group at co_base + e*CO_STRIDE
 constexpr uint32_t LIST_BYTES = LCAP * (SC_STRIDE + CO_STRIDE);
@@ -253,7 +254,7 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_ACC = 4;
 
 struct ScreenSmem {
-  uint32_t slots, list, norm, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
+  uint32_t slots, list, norm, drop, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
   uint32_t block_bytes, ext_off, slot_bytes, slot_tx;
   int nslots;
 };
@@ -264,25 +265,26 @@ __host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg) {
   s.ext_off = dblk * s.block_bytes;                 // bias extension: [2 K-chunks][rows][16 B]
   s.slot_tx = s.ext_off + rows * 32;
   s.slot_bytes = (s.slot_tx + 1023u) & ~1023u;
-  const uint32_t fixed = LIST_BYTES + 2 * 2 * BM * 4 + 512;
+  const uint32_t fixed = LIST_BYTES + 2 * 2 * BM * 4 + BM * 4 + 512;
   int n = (int)((227u * 1024u - fixed) / s.slot_bytes);
   s.nslots = n > MAX_SLOTS ? MAX_SLOTS : n;
   uint32_t off = 0;
   s.slots = off; off += (uint32_t)s.nslots * s.slot_bytes;
   s.list = off;  off += LIST_BYTES;                 // { [entry][row] float4 | [entry][row] u32 }
   s.norm = off;  off += 2 * 2 * BM * 4;             // [A buffer][loader half][row] partial ||z||^2
+  s.drop = off;  off += BM * 4;                     // [row] best score dropped from an overflowing list
   s.bars = off;  off += 512;
   s.total = off;
   return s;
 }
 
 // Candidate list maintenance (rare path).  Drops entries whose best score fell below `thr`; if
-// more than LCAP-2 survive, the entries with the lowest best score go too and the best dropped
-// score is remembered, so the row is flagged only if a dropped code could still be inside the
-// final margin.
-__device__ __noinline__ void list_compact(uint32_t sc_base, uint32_t co_base, uint32_t& psc, uint32_t& pco,
-                                          float thr, float& dropped_max) {
-  const uint32_t n = (pco - co_base) / CO_STRIDE;
+// more than LKEEP survive, the entries with the lowest best score go too and the best dropped
+// score is remembered (drop_addr: one float per row in shared memory), so the row is flagged only if
+// a dropped code could still be inside the final margin.  Returns the new entry count.  Everything
+// is passed by value: the caller's list state stays in registers.
+__device__ __noinline__ uint32_t list_compact(uint32_t sc_base, uint32_t co_base, uint32_t n, float thr,
+                                              uint32_t drop_addr) {
   uint32_t w = 0;
   for (uint32_t e = 0; e < n; ++e) {
     float a, b, c, d;
@@ -297,7 +299,7 @@ __device__ __noinline__ void list_compact(uint32_t sc_base, uint32_t co_base, ui
       ++w;
     }
   }
-  while (w > LCAP - 2) {
+  while (w > LKEEP) {
     float lo = INFINITY;              // victim: lowest best score, highest code among equals
     uint32_t lo_code = 0, lo_e = 0;
     for (uint32_t e = 0; e < w; ++e) {
@@ -308,7 +310,10 @@ __device__ __noinline__ void list_compact(uint32_t sc_base, uint32_t co_base, ui
       const float mx = fmaxf(fmaxf(a, b), fmaxf(c, d));
       if (mx < lo || (mx == lo && code > lo_code)) { lo = mx; lo_code = code; lo_e = e; }
     }
-    dropped_max = fmaxf(dropped_max, lo);
+    float dm;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dm) : "r"(drop_addr));
+    dm = fmaxf(dm, lo);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(drop_addr), "f"(dm) : "memory");
     --w;
     for (uint32_t e = lo_e; e < w; ++e) {   // close the hole, keeping entries in increasing code order
       float a, b, c, d;
@@ -319,8 +324,7 @@ __device__ __noinline__ void list_compact(uint32_t sc_base, uint32_t co_base, ui
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(co_base + e * CO_STRIDE), "r"(code) : "memory");
     }
   }
-  psc = sc_base + w * SC_STRIDE;
-  pco = co_base + w * CO_STRIDE;
+  return w;
 }
 
 struct ScreenOut {
@@ -342,11 +346,12 @@ struct ScreenOut {
 // order, so a strict '>' scan keeps the lowest code among equal scores.  Rows with exactly one
 // candidate are final; the others are queued for FP32 re-scoring.  Kept out of line (and rolled) so
 // the per-tile loop stays small in the instruction cache.
-__device__ __noinline__ void finalize_row(uint32_t sc_base, uint32_t co_base, uint32_t pco, float runmax,
-                                          float margin, float dropped_max, int n_cand, int64_t row,
-                                          const ScreenOut& out) {
+__device__ __noinline__ void finalize_row(uint32_t sc_base, uint32_t co_base, uint32_t n, float runmax,
+                                          float margin, uint32_t drop_addr, int n_cand, int64_t row,
+                                          const ScreenOut out) {
   const float thr = runmax - margin;
-  const uint32_t n = (pco - co_base) / CO_STRIDE;
+  float dropped_max;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dropped_max) : "r"(drop_addr));
   uint32_t within = 0;
   float best_s = -INFINITY;
   int best_i = -1;
@@ -433,7 +438,7 @@ __device__ __forceinline__ void load_chunk(float (&v)[32], const float* __restri
   }
 }
 
-template <int CG>
+template <int CG, bool DBG>
 __global__ void __launch_bounds__(SCREEN_THREADS, 1)
 screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_ext,
               const float* __restrict__ z, const Lay L, const float* __restrict__ e_max, float margin_scale,
@@ -628,7 +633,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     const int row_in_tile = q * 32 + lane;
     const uint32_t sc_base = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
     const uint32_t co_base = smem_base + lay.list + LCAP * SC_STRIDE + (uint32_t)row_in_tile * 4u;
-    const uint32_t co_limit = co_base + (LCAP - 2) * CO_STRIDE;   // appending 2 groups needs pco <= co_limit
+    const uint32_t drop_addr = smem_base + lay.drop + (uint32_t)row_in_tile * 4u;
     const uint32_t te_bar = (CG == 1) ? tmem_empty(0) : mapa(tmem_empty(0), 0);
     const float emax = e_max ? __ldg(e_max) : 1.f;
     uint32_t tl = 0, b = 0, b_phase = 0;
@@ -641,8 +646,8 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(norm_empty(ab));
       float runmax = -FLT_MAX;
-      float dropped_max = -FLT_MAX;
-      uint32_t psc = sc_base, pco = co_base;    // next free list entry
+      uint32_t cnt = 0;                         // list entries in use
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(drop_addr), "f"(-FLT_MAX) : "memory");
 
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(tmem_full(b), b_phase);
@@ -650,34 +655,36 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
         const int col0 = j * BN;
 
-        // One 32-column chunk of this thread's row.  Fast path: a max tree (FMNMX3).  A chunk can
-        // only contribute candidates if its maximum reaches (running max - margin); then the
-        // threshold is refreshed and every group of 4 columns whose maximum reaches it is appended
-        // (its 4 raw scores + first code) with predicated, branch-free stores.
+        // One 32-column chunk of this thread's row.  Fast path: a 16-instruction 3-input max tree.  A
+        // chunk can only contribute candidates if its maximum reaches (running max - margin); then
+        // (slow path, ~1 chunk in 5 per warp) the threshold is refreshed and every group of 4 columns
+        // whose maximum reaches it is appended (its 4 raw scores + first code) with predicated stores.
         auto process = [&](uint32_t (&ra)[32], const int cbase) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
-          if (out.dbg_scores && row < L.N) {   // diagnostic dump of the raw score tile
+          if constexpr (DBG) {
+            if (out.dbg_scores && row < L.N) {   // diagnostic dump of the raw score tile
 #pragma unroll
-            for (int i = 0; i < 32; ++i) out.dbg_scores[row * K_pad + col0 + cbase + i] = v[i];
+              for (int i = 0; i < 32; ++i) out.dbg_scores[row * K_pad + col0 + cbase + i] = v[i];
+            }
           }
-          float m4[8];
+          float t[10];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            m4[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
-          const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])),
-                                fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+          for (int i = 0; i < 10; ++i) t[i] = fmaxf(fmaxf(v[3 * i], v[3 * i + 1]), v[3 * i + 2]);
+          const float u0 = fmaxf(fmaxf(t[0], t[1]), t[2]), u1 = fmaxf(fmaxf(t[3], t[4]), t[5]);
+          const float u2 = fmaxf(fmaxf(t[6], t[7]), t[8]), u3 = fmaxf(fmaxf(t[9], v[30]), v[31]);
+          const float m = fmaxf(fmaxf(fmaxf(u0, u1), u2), u3);
           if (m >= runmax - margin) {
             // a maximum that beats the old one by more than the margin makes every listed entry stale
-            if (m > runmax + margin) { psc = sc_base; pco = co_base; }
+            if (m > runmax + margin) cnt = 0;
             runmax = fmaxf(runmax, m);
             const float thr = runmax - margin;
+            if (cnt > LKEEP) cnt = list_compact(sc_base, co_base, cnt, thr, drop_addr);
+            uint32_t psc = sc_base + cnt * SC_STRIDE, pco = co_base + cnt * CO_STRIDE;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if ((i & 1) == 0) {
-                if (pco > co_limit) list_compact(sc_base, co_base, psc, pco, thr, dropped_max);
-              }
+              const float m4 = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
               asm volatile(
                   "{\n\t"
                   ".reg .pred p;\n\t"
@@ -688,10 +695,11 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
                   "@p add.u32 %1, %1, %10;\n\t"
                   "}"
                   : "+r"(psc), "+r"(pco)
-                  : "f"(m4[i]), "f"(thr), "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]),
+                  : "f"(m4), "f"(thr), "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]),
                     "r"((uint32_t)(col0 + cbase + 4 * i)), "n"(SC_STRIDE), "n"(CO_STRIDE)
                   : "memory");
             }
+            cnt = (pco - co_base) / CO_STRIDE;
           }
         };
 
@@ -715,7 +723,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
       }
 
-      if (row < L.N) finalize_row(sc_base, co_base, pco, runmax, margin, dropped_max, n_cand, row, out);
+      if (row < L.N) finalize_row(sc_base, co_base, cnt, runmax, margin, drop_addr, n_cand, row, out);
     }
   }
 
@@ -776,7 +784,7 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
   CUtensorMap mb, mx;
   if (int rc = make_map(enc, &mb, E_bf16, K_pad, D + SCREEN_EXT, 64, BN / CG, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_map(enc, &mx, E_bf16, K_pad, D + SCREEN_EXT, 8, BN / CG, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-  auto kern = screen_kernel<CG>;
+  auto kern = out.dbg_cand ? screen_kernel<CG, true> : screen_kernel<CG, false>;
   if (int rc = enable_smem(kern, lay.total)) return rc;
   const int64_t rows_per_group = (int64_t)BM * CG;
   const int64_t group_tiles = (L.N + rows_per_group - 1) / rows_per_group;
