@@ -778,7 +778,7 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
                          cudaStream_t st) {
   const int dblk = D / 64;
   const ScreenSmem lay = screen_smem_layout(dblk, CG);
-  CCVSQ_REQUIRE(lay.nslots >= 2, CCVSQ_UNSUPPORTED, "screen: D=%d leaves room for %d B slots", D, lay.nslots);
+  CCVSQ_REQUIRE(lay.nslots >= 1, CCVSQ_UNSUPPORTED, "screen: D=%d leaves room for %d B slots", D, lay.nslots);
   EncodeTiledFn enc;
   if (int rc = get_encode_fn(&enc)) return rc;
   CUtensorMap mb, mx;
