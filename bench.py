@@ -214,7 +214,7 @@ def main():
     from ccvs_b200 import VectorQuantizer, ops
     from ccvs_b200.quantize import EMAVectorQuantizer
 
-    (clips, frames), D, h, w, K, desc = WORKLOADS[args.workload]
+    (clips, frames), D, h, w_, K, desc = WORKLOADS[args.workload]
     z, cb, n_lat = make_inputs(args.workload, dev, 1234 + rank)
     train = args.workload == "train"
     if train:
@@ -237,7 +237,7 @@ def main():
             return idx, loss, perp, zin.grad
         with torch.no_grad():
             z_q, loss, (perp, _, idx) = vq(zin)
-            dec = vq.embed_code(idx.view(clips * frames, h, w))
+            dec = vq.embed_code(idx.view(clips * frames, h, w_))
         return idx, loss, perp, dec
 
     def barrier():
@@ -279,10 +279,29 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["note"] = f"sampled from warm-up through the timed region plus {extra_steps} identical untimed steps"
-    # per-kernel breakdown: separate pass with every entry point bracketed by events
+    # per-kernel breakdown: a separate, untimed-for-`value` pass that issues the same kernels through the
+    # step-by-step entry points of the C ABI, each bracketed by events (the product path above makes one
+    # composite call per forward / backward, which cannot be bracketed kernel by kernel)
+    lay = ops.layout_of(z.shape, D, 1)
+    w = vq.embedding.weight.detach()
+    zd = z.detach()
+    g_one = torch.ones((), device=dev)
+
+    def breakdown_step():
+        pcb = ops.prepare_codebook(w)
+        idx = ops.search(zd, lay, pcb, mode=args.search_mode)
+        _, sq, counts = ops.assign(zd, lay, w, idx)
+        ops.finalize(K, D, float(zd.numel()), float(n_lat), 0.25, counts=counts, sq_err=sq, want_loss=True, want_perplexity=True)
+        if train:
+            ops.timed("ccvsq_quantize_backward", lambda: ops.quantize_backward(zd, lay, w, idx, g_out, g_one, 0.25))
+            resid, _ = ops.code_stats(zd, lay, w, K, idx, sub=1.0, want_counts=False)
+            ops.ema_update(w.clone(), vq.ema_count.clone(), vq.ema_sum.clone(), resid, counts, 0.99, 1e-5)
+        else:
+            ops.gather(idx.view(clips * frames, h, w_), w)
+
     ops.PROFILER.reset(timing=True)
     for _ in range(args.steps):
-        step(z)
+        breakdown_step()
     torch.cuda.synchronize()
     prof = ops.PROFILER.summary()
     ops.PROFILER.reset(timing=False)
@@ -362,6 +381,11 @@ def main():
         calls, tms = prof["ccvsq_assign"]
         gbs = n_lat * (8 * D + 8) / (tms / calls * 1e-3) / 1e9
         extra["assign"] = {"achieved_GBs": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "ms_per_launch": tms / calls}
+    if "ccvsq_quantize_backward" in prof:
+        calls, tms = prof["ccvsq_quantize_backward"]
+        gbs = n_lat * (12 * D + 8) / (tms / calls * 1e-3) / 1e9
+        extra["backward_dz_plus_code_stats"] = {"achieved_GBs": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "ms_per_launch": tms / calls,
+                                                "note": "memset + fused dz / per-code scatter-reduce kernel + dE scale"}
 
     cpu = None if args.no_cpu_baseline or world > 1 else cpu_baseline(args.workload)
 
@@ -370,7 +394,7 @@ def main():
         "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "K": K, "D": D, "latents_per_gpu": n_lat,
-                   "layout": [clips, frames, D, h, w], "distribution": "T (E~N(0,1), z=E[randint]+0.5N(0,1))",
+                   "layout": [clips, frames, D, h, w_], "distribution": "T (E~N(0,1), z=E[randint]+0.5N(0,1))",
                    "search_mode": args.search_mode, "screen_operands": "bf16 (fp32 accumulate), fp32 rescoring",
                    "l2": f"inputs larger than L2 ({z.numel() * 4 / 2**20:.0f} MiB of latents per step)",
                    "parallelism": f"frame-sharded x{world}, codebook replicated, no data-path collective"},

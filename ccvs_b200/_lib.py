@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libccvsq.so")
@@ -40,6 +40,23 @@ class Layout(Structure):
         return self.C // self.mult
 
 
+class ForwardArgs(Structure):
+    """struct ccvsq_forward_args — see include/ccvsq.h."""
+
+    _fields_ = [
+        ("z", c_void_p), ("lay", Layout), ("E", c_void_p), ("K", c_int32), ("beta", c_float),
+        ("search_mode", c_int32), ("n_cand", c_int32), ("margin_tau", c_float), ("exact_fallback", c_int32),
+        ("indices_only", c_int32), ("prepare", c_int32),
+        ("e_sq", c_void_p), ("E_bf16", c_void_p), ("e_max", c_void_p),
+        ("header", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_uint64),
+        ("idx", c_void_p), ("zq", c_void_p), ("loss", c_void_p), ("perplexity", c_void_p),
+        ("ev_search_begin", c_void_p), ("ev_search_end", c_void_p),
+    ]
+
+
+HEADER_INTS = 16
+SEARCH_MODES = {"auto": 0, "tensor": 1, "exact": 2}
+
 # name -> (restype, argtypes); every symbol include/ccvsq.h declares.
 _P = c_void_p
 SIGNATURES = {
@@ -59,6 +76,9 @@ SIGNATURES = {
     "ccvsq_code_stats": (c_int, [_P, Layout, _P, c_int, _P, c_float, _P, _P, _P]),
     "ccvsq_finalize": (c_int, [_P, _P, _P, _P, c_int, c_int, c_double, c_double, c_float, _P, _P, _P, _P]),
     "ccvsq_ema_update": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
+    "ccvsq_forward_workspace_bytes": (c_uint64, [c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "ccvsq_quantize_forward": (c_int, [POINTER(ForwardArgs), _P]),
+    "ccvsq_quantize_backward": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, c_float, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -98,4 +98,41 @@ constexpr int SCREEN_EXT = 16;
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---------------------------------------------------------------------------------------------
+// HBM-bound stream kernels: argument block shared by the generic (stream_kernels.cu) and the
+// 128-bit fast paths (stream_fast.cu)
+// ---------------------------------------------------------------------------------------------
+enum { MODE_ASSIGN = 0, MODE_BACKWARD = 1, MODE_GATHER = 2, MODE_STATS = 3 };
+
+struct FinArgs {          // loss / perplexity folded into the assign kernel (last CTA); ticket NULL = off
+  int32_t* ticket;        // zeroed by the caller
+  float* loss;
+  float* perplexity;
+  double M, N;
+  float beta;
+};
+
+struct StreamArgs {
+  const float* x;         // latents (assign / backward / stats); unused by gather
+  const float* g;         // backward: upstream gradient of z_q (may be NULL)
+  const float* E;         // codebook [K, D]
+  const int64_t* idx;     // codes, one per latent row
+  float* out;             // z_q / dz / decoded latents (may be NULL)
+  double* sq_err;         // assign
+  int32_t* counts;        // assign / stats
+  float* resid;           // stats, or backward with the scatter-reduce fused in
+  const float* g_loss;    // backward: device scalar
+  float coef_scale;       // backward: 2 / M
+  float sub;              // stats: resid += x - sub * E[idx]
+  int32_t* err_flag;      // gather
+  int K;
+  FinArgs fin;
+};
+
+bool stream_fast_supported(const StreamArgs& a, const Lay& L);
+int stream_fast_launch(int mode, const StreamArgs& a, const Lay& L, cudaStream_t st);
+// generic launches + finalize (stream_kernels.cu), used by the ABI entry points and the composites
+int stream_launch(int mode, const StreamArgs& a, const Lay& L, cudaStream_t st);
+int prepare_codebook_launch(const float* E, int K, int D, float* e_sq, void* E_bf16, float* e_max, cudaStream_t st);
+
 }  // namespace ccvsq

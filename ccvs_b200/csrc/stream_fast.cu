@@ -1,0 +1,364 @@
+// stream_fast.cu — 128-bit fast paths of the HBM-bound kernels (assign / decode gather / backward /
+// per-code scatter-reduce).  Same arithmetic as the generic kernels in stream_kernels.cu; these are
+// taken whenever the layout allows 16-byte accesses (the generic ones stay as the fallback for odd
+// shapes: e_dim = 1, S % 4 != 0, C % 32 != 0, unaligned views).
+//
+// Channel-major latents (S > 1: NCHW / NTCHW, element (g,c,s) at (g*C + c)*S + s)
+//   A CTA owns 32 consecutive positions x one slab of <= 256 channels.  Every thread works on 4x4
+//   blocks (4 consecutive positions x 4 consecutive channels):
+//     * the latent side of a block is 4 LDG.128 along the spatial index (coalesced: 8 lanes cover the
+//       128 contiguous bytes of one channel), issued first so they are in flight during the gather;
+//     * the codebook side is gathered once per tile: E[idx[p]] rows are read with LDG.128 along the
+//       channel index and parked in shared memory as [position][16-byte chunk], chunk index XOR-
+//       swizzled with (position/4) so both the row-wise fill and the block-wise read (4 LDS.128, one
+//       per position) are bank-conflict free without padding;
+//     * the 4x4 transpose between "channels of a position" (codebook rows, atomics) and "positions of
+//       a channel" (tensor I/O) happens in registers.
+//   Per 64 KiB of HBM traffic the LSU sees 5 full-width passes (z load, E load, E park, E read, store)
+//   instead of the 7 passes + 4-byte accesses of the generic tile kernels.
+// Row-major latents (S == 1): rows are contiguous; a flat loop over 16-byte chunks, no shared memory.
+#include <math.h>
+#include "common.cuh"
+
+namespace ccvsq {
+
+constexpr int FPT = 32;    // positions per tile
+constexpr int FNT = 256;   // threads per CTA
+constexpr int FSLAB = 256; // channels per CTA (a tile is FPT x slab)
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// loss / perplexity by the last CTA to finish (replaces the separate finalize launch in forward)
+__device__ void fold_finalize(const StreamArgs& a, unsigned total_ctas, bool* s_last, float* s_red) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *s_last = atomicAdd(a.fin.ticket, 1) == (int)(total_ctas - 1);
+  __syncthreads();
+  if (!*s_last) return;
+  __threadfence();
+  if (a.fin.loss && threadIdx.x == 0) {
+    const double sq = atomicAdd(a.sq_err, 0.0);         // coherent read of the accumulator
+    const float mse = (float)(sq / a.fin.M);            // quantize.py:60-61
+    *a.fin.loss = mse + a.fin.beta * mse;
+  }
+  if (a.fin.perplexity && a.counts) {
+    float acc = 0.f;
+    for (int k = threadIdx.x; k < a.K; k += FNT) {
+      const float p = (float)((double)__ldcg(a.counts + k) / a.fin.N);
+      acc += p * logf(p + 1e-10f);                      // quantize.py:68
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < FNT / 32; ++w) s += s_red[w];
+      *a.fin.perplexity = expf(-s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel-major tiles
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int MAXIT>
+__global__ void __launch_bounds__(FNT) cm4_kernel(const StreamArgs a, const Lay L, const int CS) {
+  extern __shared__ float4 tile4[];                 // [FPT][CS/4], chunk index ^ (position/4)
+  __shared__ float s_red[FNT / 32];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const int64_t p0 = (int64_t)blockIdx.x * FPT;
+  const int np = (int)min((int64_t)FPT, L.P - p0);
+  const int c_lo = (int)blockIdx.y * CS;
+  const int QS = CS >> 2;                           // 16-byte chunks per tile row
+  const int nblk = 8 * QS;                          // 4x4 blocks in the tile
+  constexpr bool HAS_X = MODE != MODE_GATHER;
+  const bool has_g = MODE == MODE_BACKWARD && a.g != nullptr;
+  const bool need_e = MODE != MODE_STATS || a.sub != 0.f;
+
+  // ---- streaming loads first (independent of the gather below)
+  float xa[MAXIT][4][4], ga[MAXIT][4][4];           // [it][channel j][position i]
+  int64_t base[MAXIT];
+  bool valid[MAXIT];
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    const int b = tid + it * FNT;
+    const int p4 = b & 7, cq = b >> 3;
+    valid[it] = b < nblk && 4 * p4 < np;
+    base[it] = 0;
+    if (valid[it]) {
+      const int64_t pos = p0 + 4 * p4;
+      const int64_t g = pos / L.S;
+      const int s = (int)(pos - g * L.S);
+      base[it] = (g * L.C + c_lo + 4 * cq) * (int64_t)L.S + s;
+      if (HAS_X) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(xa[it][j]) = __ldcs(reinterpret_cast<const float4*>(a.x + base[it] + (int64_t)j * L.S));
+      }
+      if (has_g) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(ga[it][j]) = __ldcs(reinterpret_cast<const float4*>(a.g + base[it] + (int64_t)j * L.S));
+      }
+    }
+  }
+
+  // ---- gather the codebook rows of this tile into shared memory
+  if (need_e) {
+    const int total = np * QS;
+    for (int i = tid; i < total; i += FNT) {
+      const int p = i / QS, q = i - p * QS;
+      const int c = c_lo + 4 * q;
+      const int m = c / L.D, j = c - m * L.D;
+      int64_t k = __ldg(a.idx + (p0 + p) * L.mult + m);
+      if (k < 0 || k >= a.K) {
+        if (MODE == MODE_GATHER && a.err_flag) atomicOr(a.err_flag, 1);
+        k = k < 0 ? 0 : a.K - 1;
+        if (MODE == MODE_GATHER) k = 0;
+      }
+      tile4[p * QS + (q ^ ((p >> 2) & 7))] = __ldg(reinterpret_cast<const float4*>(a.E + (size_t)k * L.D + j));
+    }
+  }
+  if (a.counts && blockIdx.y == 0 && (MODE == MODE_ASSIGN || MODE == MODE_STATS)) {
+    const int rows = np * L.mult;
+    for (int r = tid; r < rows; r += FNT) {
+      int64_t k = __ldg(a.idx + p0 * L.mult + r);
+      if (MODE == MODE_ASSIGN) k = k < 0 ? 0 : (k >= a.K ? a.K - 1 : k);
+      if (k >= 0 && k < a.K) atomicAdd(a.counts + k, 1);
+    }
+  }
+  __syncthreads();
+
+  float coef = 0.f;
+  if (MODE == MODE_BACKWARD) coef = __ldg(a.g_loss) * a.coef_scale;
+  float acc = 0.f;
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it) {
+    if (!valid[it]) continue;
+    const int b = tid + it * FNT;
+    const int p4 = b & 7, cq = b >> 3;
+    float ea[4][4];                                 // [position i][channel j]
+    if (need_e) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(ea[i]) = tile4[(4 * p4 + i) * QS + (cq ^ p4)];
+    }
+    float oa[4][4];                                 // [channel j][position i]
+    if (MODE == MODE_ASSIGN) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float diff = __fsub_rn(ea[i][j], xa[it][j][i]);     // fl(E[idx] - z)
+          oa[j][i] = __fadd_rn(xa[it][j][i], diff);                 // fl(z + fl(E[idx] - z))  (quantize.py:64)
+          acc = fmaf(diff, diff, acc);
+        }
+    } else if (MODE == MODE_BACKWARD) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float t = __fmul_rn(coef, __fsub_rn(xa[it][j][i], ea[i][j]));
+          oa[j][i] = has_g ? __fadd_rn(t, ga[it][j][i]) : t;
+        }
+    } else if (MODE == MODE_GATHER) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oa[j][i] = ea[i][j];
+    }
+    if (MODE != MODE_STATS && a.out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4* dst = reinterpret_cast<float4*>(a.out + base[it] + (int64_t)j * L.S);
+        const float4 v = *reinterpret_cast<const float4*>(oa[j]);
+        if (MODE == MODE_GATHER) __stcs(dst, v); else *dst = v;
+      }
+    }
+    if ((MODE == MODE_STATS || MODE == MODE_BACKWARD) && a.resid) {
+      const int c = c_lo + 4 * cq;
+      const int m = c / L.D, j0 = c - m * L.D;
+      const float sub = MODE == MODE_BACKWARD ? 1.f : a.sub;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t k = __ldg(a.idx + (p0 + 4 * p4 + i) * L.mult + m);
+        if (k < 0 || k >= a.K) continue;
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = need_e ? xa[it][j][i] - sub * ea[i][j] : xa[it][j][i];
+        red_add_v4(a.resid + (size_t)k * L.D + j0, r[0], r[1], r[2], r[3]);
+      }
+    }
+  }
+
+  if (MODE == MODE_ASSIGN && a.sq_err) {
+    acc = warp_sum(acc);
+    if ((tid & 31) == 0) s_red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < FNT / 32; ++w) s += s_red[w];
+      atomicAdd(a.sq_err, (double)s);
+    }
+  }
+  if (MODE == MODE_ASSIGN && a.fin.ticket) fold_finalize(a, gridDim.x * gridDim.y, &s_last, s_red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-major latents: flat loop over 16-byte chunks, U chunks per thread
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(FNT) rows4_kernel(const StreamArgs a, const int64_t N, const int D) {
+  __shared__ float s_red[FNT / 32];
+  __shared__ bool s_last;
+  constexpr int U = 4;
+  const int Q = D >> 2;
+  const int64_t total = N * Q;
+  const int64_t cb = (int64_t)blockIdx.x * (U * FNT);      // first chunk of this CTA
+  const int64_t row_b = cb / Q;
+  const int q_b = (int)(cb - row_b * Q);
+  const bool has_g = MODE == MODE_BACKWARD && a.g != nullptr;
+  const bool need_e = MODE != MODE_STATS || a.sub != 0.f;
+
+  int64_t row[U];
+  int q[U];
+  int64_t k[U];
+  bool valid[U];
+  float4 xv[U], gv[U], ev[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int o = (int)threadIdx.x + u * FNT;
+    valid[u] = cb + o < total;
+    const int oo = o + q_b;
+    const int dr = oo / Q;
+    row[u] = row_b + dr;
+    q[u] = oo - dr * Q;
+    k[u] = 0;
+    if (valid[u]) {
+      if (MODE != MODE_GATHER) xv[u] = __ldcs(reinterpret_cast<const float4*>(a.x) + cb + o);
+      if (has_g) gv[u] = __ldcs(reinterpret_cast<const float4*>(a.g) + cb + o);
+      k[u] = __ldg(a.idx + row[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!valid[u]) continue;
+    bool in_range = k[u] >= 0 && k[u] < a.K;
+    if (!in_range) {
+      if (MODE == MODE_GATHER) { if (a.err_flag) atomicOr(a.err_flag, 1); k[u] = 0; }
+      else if (MODE != MODE_STATS) { k[u] = k[u] < 0 ? 0 : a.K - 1; in_range = true; }
+    }
+    if (need_e && (in_range || MODE == MODE_GATHER))
+      ev[u] = __ldg(reinterpret_cast<const float4*>(a.E + (size_t)k[u] * D) + q[u]);
+    if (MODE == MODE_STATS && !in_range) valid[u] = false;
+  }
+  float coef = 0.f;
+  if (MODE == MODE_BACKWARD) coef = __ldg(a.g_loss) * a.coef_scale;
+  float acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!valid[u]) continue;
+    const int o = (int)threadIdx.x + u * FNT;
+    float x[4], e[4], g[4], out[4];
+    if (MODE != MODE_GATHER) *reinterpret_cast<float4*>(x) = xv[u];
+    if (need_e) *reinterpret_cast<float4*>(e) = ev[u];
+    if (has_g) *reinterpret_cast<float4*>(g) = gv[u];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (MODE == MODE_ASSIGN) {
+        const float diff = __fsub_rn(e[j], x[j]);
+        out[j] = __fadd_rn(x[j], diff);
+        acc = fmaf(diff, diff, acc);
+      } else if (MODE == MODE_BACKWARD) {
+        const float t = __fmul_rn(coef, __fsub_rn(x[j], e[j]));
+        out[j] = has_g ? __fadd_rn(t, g[j]) : t;
+      } else if (MODE == MODE_GATHER) {
+        out[j] = e[j];
+      }
+    }
+    if (MODE != MODE_STATS && a.out) {
+      float4* dst = reinterpret_cast<float4*>(a.out) + cb + o;
+      const float4 v = *reinterpret_cast<const float4*>(out);
+      if (MODE == MODE_GATHER) __stcs(dst, v); else *dst = v;
+    }
+    if ((MODE == MODE_STATS || MODE == MODE_BACKWARD) && a.resid) {
+      const float sub = MODE == MODE_BACKWARD ? 1.f : a.sub;
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = need_e ? x[j] - sub * e[j] : x[j];
+      red_add_v4(a.resid + (size_t)k[u] * D + 4 * q[u], r[0], r[1], r[2], r[3]);
+    }
+    if (a.counts && q[u] == 0 && (MODE == MODE_ASSIGN || MODE == MODE_STATS)) atomicAdd(a.counts + k[u], 1);
+  }
+  if (MODE == MODE_ASSIGN && a.sq_err) {
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < FNT / 32; ++w) s += s_red[w];
+      atomicAdd(a.sq_err, (double)s);
+    }
+  }
+  if (MODE == MODE_ASSIGN && a.fin.ticket) fold_finalize(a, gridDim.x, &s_last, s_red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+bool stream_fast_supported(const StreamArgs& a, const Lay& L) {
+  if (!aligned16(a.x) || !aligned16(a.g) || !aligned16(a.E) || !aligned16(a.out) || !aligned16(a.resid)) return false;
+  if (L.D % 4 != 0) return false;
+  if (L.S == 1) return true;
+  if (L.S % 4 != 0 || L.C % 32 != 0) return false;
+  const int nslab = (L.C + FSLAB - 1) / FSLAB;
+  if (L.C % nslab != 0) return false;
+  const int CS = L.C / nslab;
+  return CS % 32 == 0;
+}
+
+template <int MODE>
+static int launch_cm4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
+  const int nslab = (L.C + FSLAB - 1) / FSLAB;
+  const int CS = L.C / nslab;
+  const size_t smem = (size_t)FPT * CS * sizeof(float);
+  const dim3 grid((unsigned)cdiv(L.P, FPT), (unsigned)nslab);
+  if (CS <= 128) {
+    cm4_kernel<MODE, 1><<<grid, FNT, smem, st>>>(a, L, CS);
+  } else {
+    cm4_kernel<MODE, 2><<<grid, FNT, smem, st>>>(a, L, CS);
+  }
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+template <int MODE>
+static int launch_rows4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
+  const int64_t total = L.N * (L.D >> 2);
+  const int64_t blocks = (total + 4 * FNT - 1) / (4 * FNT);
+  CCVSQ_REQUIRE(blocks < (1ll << 31), CCVSQ_BAD_SHAPE, "stream kernel: %lld CTAs exceed the grid limit", (long long)blocks);
+  rows4_kernel<MODE><<<(unsigned)blocks, FNT, 0, st>>>(a, L.N, L.D);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+int stream_fast_launch(int mode, const StreamArgs& a, const Lay& L, cudaStream_t st) {
+  const bool cm = L.S > 1;
+  switch (mode) {
+    case MODE_ASSIGN:   return cm ? launch_cm4<MODE_ASSIGN>(a, L, st) : launch_rows4<MODE_ASSIGN>(a, L, st);
+    case MODE_BACKWARD: return cm ? launch_cm4<MODE_BACKWARD>(a, L, st) : launch_rows4<MODE_BACKWARD>(a, L, st);
+    case MODE_GATHER:   return cm ? launch_cm4<MODE_GATHER>(a, L, st) : launch_rows4<MODE_GATHER>(a, L, st);
+    case MODE_STATS:    return cm ? launch_cm4<MODE_STATS>(a, L, st) : launch_rows4<MODE_STATS>(a, L, st);
+  }
+  set_error("stream_fast_launch: bad mode %d", mode);
+  return CCVSQ_BAD_SHAPE;
+}
+
+}  // namespace ccvsq

@@ -370,12 +370,12 @@ __global__ void __launch_bounds__(NT) gather_cm_kernel(const int64_t* __restrict
 // ------------------------------------------------------------------------------------------------
 // finalize: dE, loss, perplexity
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ resid,
+__global__ void __launch_bounds__(256) finalize_kernel(const float* resid,   /* may alias dE */
                                                        const int32_t* __restrict__ counts,
                                                        const double* __restrict__ sq_err,
                                                        const float* __restrict__ g_loss, int K, int D,
                                                        double M, double N, float beta,
-                                                       float* __restrict__ dE, float* __restrict__ loss,
+                                                       float* dE, float* __restrict__ loss,
                                                        float* __restrict__ perplexity) {
   if (dE && resid) {
     const float coef = -(float)(2.0 * (double)beta / M) * __ldg(g_loss);
@@ -454,18 +454,25 @@ __global__ void ema_embed_kernel(float* __restrict__ E, const float* __restrict_
 // =================================================================================================
 using namespace ccvsq;
 
-extern "C" int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf16, float* e_max,
-                                      void* stream) {
-  CCVSQ_REQUIRE(E && e_sq, CCVSQ_NULL_POINTER, "prepare_codebook: E and e_sq must be non-null");
-  CCVSQ_REQUIRE(K > 0 && D > 0, CCVSQ_BAD_SHAPE, "prepare_codebook: K=%d D=%d", K, D);
-  cudaStream_t st = (cudaStream_t)stream;
+namespace ccvsq {
+// *e_max (if given) must already be zero
+int prepare_codebook_launch(const float* E, int K, int D, float* e_sq, void* E_bf16, float* e_max, cudaStream_t st) {
   const int K_pad = E_bf16 ? ccvsq_codebook_rows(K) : K;
-  if (e_max) CCVSQ_CUDA(cudaMemsetAsync(e_max, 0, sizeof(float), st));
   const int wpb = 8;
   prepare_codebook_kernel<<<cdiv(K_pad, wpb), wpb * 32, 0, st>>>(E, K, K_pad, D, e_sq, (__nv_bfloat16*)E_bf16,
                                                                  (unsigned int*)e_max);
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
+}
+}  // namespace ccvsq
+
+extern "C" int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf16, float* e_max,
+                                      void* stream) {
+  CCVSQ_REQUIRE(E && e_sq, CCVSQ_NULL_POINTER, "prepare_codebook: E and e_sq must be non-null");
+  CCVSQ_REQUIRE(K > 0 && D > 0, CCVSQ_BAD_SHAPE, "prepare_codebook: K=%d D=%d", K, D);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (e_max) CCVSQ_CUDA(cudaMemsetAsync(e_max, 0, sizeof(float), st));
+  return prepare_codebook_launch(E, K, D, e_sq, E_bf16, e_max, st);
 }
 
 extern "C" int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, const float* e_sq, int K,
@@ -490,33 +497,80 @@ extern "C" int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, c
   return CCVSQ_OK;
 }
 
+// generic (any layout) or 128-bit fast path (stream_fast.cu), same arithmetic
+namespace ccvsq {
+int stream_launch(int mode, const StreamArgs& a, const Lay& L, cudaStream_t st) {
+  if (stream_fast_supported(a, L)) return stream_fast_launch(mode, a, L, st);
+  const unsigned tiles = (unsigned)cdiv(L.P, PT);
+  const size_t smem = tile_smem_bytes(L);
+  switch (mode) {
+    case MODE_ASSIGN:
+      if (int rc = enable_smem(assign_kernel, smem)) return rc;
+      assign_kernel<<<tiles, NT, smem, st>>>(a.x, L, a.E, a.K, a.idx, a.out, a.sq_err, a.counts);
+      break;
+    case MODE_BACKWARD:
+      if (a.out) {
+        if (int rc = enable_smem(backward_dz_kernel, smem)) return rc;
+        backward_dz_kernel<<<tiles, NT, smem, st>>>(a.x, L, a.E, a.K, a.idx, a.g, a.g_loss, a.coef_scale, a.out);
+        CCVSQ_LAUNCH_CHECK();
+      }
+      if (a.resid) {
+        if (int rc = enable_smem(code_stats_kernel, smem)) return rc;
+        code_stats_kernel<<<tiles, NT, smem, st>>>(a.x, L, a.E, a.K, a.idx, 1.f, a.resid, nullptr);
+      }
+      break;
+    case MODE_STATS:
+      if (int rc = enable_smem(code_stats_kernel, smem)) return rc;
+      code_stats_kernel<<<tiles, NT, smem, st>>>(a.x, L, a.E, a.K, a.idx, a.sub, a.resid, a.counts);
+      break;
+    case MODE_GATHER:
+      if (L.S == 1) {
+        const int64_t warps_needed = (L.N + 3) / 4;
+        const int64_t blocks = (warps_needed + NW - 1) / NW;
+        CCVSQ_REQUIRE(blocks < (1ll << 31), CCVSQ_BAD_SHAPE, "gather: N=%lld too large", (long long)L.N);
+        gather_rows_kernel<false><<<(unsigned)blocks, NT, 0, st>>>(a.idx, a.E, a.K, L.D, L.N, a.out, a.err_flag);
+      } else {
+        if (int rc = enable_smem(gather_cm_kernel, smem)) return rc;
+        gather_cm_kernel<<<tiles, NT, smem, st>>>(a.idx, a.E, a.K, L, a.out, a.err_flag);
+      }
+      break;
+    default:
+      set_error("stream_launch: bad mode %d", mode);
+      return CCVSQ_BAD_SHAPE;
+  }
+  CCVSQ_LAUNCH_CHECK();
+  // the generic assign kernel has no folded finalize: one extra (tiny) launch
+  if (mode == MODE_ASSIGN && a.fin.ticket && (a.fin.loss || a.fin.perplexity)) {
+    finalize_kernel<<<1, 256, 0, st>>>(nullptr, a.counts, a.sq_err, nullptr, a.K, L.D, a.fin.M, a.fin.N, a.fin.beta,
+                                      nullptr, a.fin.loss, a.fin.perplexity);
+    CCVSQ_LAUNCH_CHECK();
+  }
+  return CCVSQ_OK;
+}
+}  // namespace ccvsq
+
 extern "C" int ccvsq_assign(const float* z, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
                             float* zq_out, double* sq_err, int32_t* counts, void* stream) {
   CCVSQ_REQUIRE(z && E && idx, CCVSQ_NULL_POINTER, "assign: null pointer");
   CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "assign: K=%d", K);
   Lay L;
   if (int rc = make_lay(lay, &L)) return rc;
-  const size_t smem = tile_smem_bytes(L);
-  if (int rc = enable_smem(assign_kernel, smem)) return rc;
-  assign_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(z, L, E, K, idx, zq_out,
-                                                                          sq_err, counts);
-  CCVSQ_LAUNCH_CHECK();
-  return CCVSQ_OK;
+  StreamArgs a = {};
+  a.x = z; a.E = E; a.idx = idx; a.out = zq_out; a.sq_err = sq_err; a.counts = counts; a.K = K;
+  return stream_launch(MODE_ASSIGN, a, L, (cudaStream_t)stream);
 }
 
 extern "C" int ccvsq_backward_dz(const float* z, ccvsq_layout lay, const float* E, int K,
                                  const int64_t* idx, const float* g_zq, const float* g_loss, float* dz,
                                  void* stream) {
   CCVSQ_REQUIRE(z && E && idx && g_loss && dz, CCVSQ_NULL_POINTER, "backward_dz: null pointer");
+  CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "backward_dz: K=%d", K);
   Lay L;
   if (int rc = make_lay(lay, &L)) return rc;
-  const size_t smem = tile_smem_bytes(L);
-  if (int rc = enable_smem(backward_dz_kernel, smem)) return rc;
-  const double M = (double)L.P * L.C;
-  backward_dz_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(
-      z, L, E, K, idx, g_zq, g_loss, (float)(2.0 / M), dz);
-  CCVSQ_LAUNCH_CHECK();
-  return CCVSQ_OK;
+  StreamArgs a = {};
+  a.x = z; a.g = g_zq; a.E = E; a.idx = idx; a.out = dz; a.g_loss = g_loss; a.K = K;
+  a.coef_scale = (float)(2.0 / ((double)L.P * L.C));
+  return stream_launch(MODE_BACKWARD, a, L, (cudaStream_t)stream);
 }
 
 extern "C" int ccvsq_code_stats(const float* x, ccvsq_layout lay, const float* E, int K,
@@ -524,14 +578,12 @@ extern "C" int ccvsq_code_stats(const float* x, ccvsq_layout lay, const float* E
                                 void* stream) {
   CCVSQ_REQUIRE(x && idx && resid, CCVSQ_NULL_POINTER, "code_stats: null pointer");
   CCVSQ_REQUIRE(sub == 0.f || E, CCVSQ_NULL_POINTER, "code_stats: E required when sub != 0");
+  CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "code_stats: K=%d", K);
   Lay L;
   if (int rc = make_lay(lay, &L)) return rc;
-  const size_t smem = tile_smem_bytes(L);
-  if (int rc = enable_smem(code_stats_kernel, smem)) return rc;
-  code_stats_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(x, L, E, K, idx, sub,
-                                                                              resid, counts);
-  CCVSQ_LAUNCH_CHECK();
-  return CCVSQ_OK;
+  StreamArgs a = {};
+  a.x = x; a.E = E; a.idx = idx; a.resid = resid; a.counts = counts; a.sub = sub; a.K = K;
+  return stream_launch(MODE_STATS, a, L, (cudaStream_t)stream);
 }
 
 extern "C" int ccvsq_gather(const int64_t* code, const float* E, int K, ccvsq_layout out_lay, float* out,
@@ -540,24 +592,9 @@ extern "C" int ccvsq_gather(const int64_t* code, const float* E, int K, ccvsq_la
   CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "gather: K=%d", K);
   Lay L;
   if (int rc = make_lay(out_lay, &L)) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (L.S == 1) {
-    const int64_t warps_needed = (L.N + 3) / 4;
-    int64_t blocks = (warps_needed + NW - 1) / NW;
-    const int64_t cap = (int64_t)kNumSMs * 8 * 4;   // grid-stride beyond a few waves
-    if (blocks > cap) blocks = cap;
-    const bool vec = (L.D % 4 == 0) && (((uintptr_t)E | (uintptr_t)out) % 16 == 0);
-    if (vec)
-      gather_rows_kernel<true><<<(unsigned)blocks, NT, 0, st>>>(code, E, K, L.D, L.N, out, err_flag);
-    else
-      gather_rows_kernel<false><<<(unsigned)blocks, NT, 0, st>>>(code, E, K, L.D, L.N, out, err_flag);
-  } else {
-    const size_t smem = tile_smem_bytes(L);
-    if (int rc = enable_smem(gather_cm_kernel, smem)) return rc;
-    gather_cm_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, st>>>(code, E, K, L, out, err_flag);
-  }
-  CCVSQ_LAUNCH_CHECK();
-  return CCVSQ_OK;
+  StreamArgs a = {};
+  a.E = E; a.idx = code; a.out = out; a.err_flag = err_flag; a.K = K;
+  return stream_launch(MODE_GATHER, a, L, (cudaStream_t)stream);
 }
 
 extern "C" int ccvsq_finalize(const float* resid, const int32_t* counts, const double* sq_err,

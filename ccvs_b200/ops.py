@@ -23,6 +23,7 @@ _KERNELS_PER_CALL = {
     "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
     "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1, "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1,
     "ccvsq_finalize": 1, "ccvsq_ema_update": 2,
+    "ccvsq_quantize_forward": 0, "ccvsq_quantize_backward": 0,   # composites: counted by their wrappers
 }
 
 
@@ -66,6 +67,19 @@ def _call(name: str, *args) -> None:
         rc = fn(*args)
     PROFILER.launches += _KERNELS_PER_CALL[name]
     _lib.check(rc, name)
+
+
+def timed(name: str, fn):
+    """Bracket a composite wrapper with events when the profiler is timing everything."""
+    if PROFILER.timing is not True:
+        return fn()
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    out = fn()
+    e.record()
+    PROFILER.records.append((name, s, e))
+    return out
 
 
 def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
@@ -331,6 +345,106 @@ def finalize(K: int, D: int, M: float, N: float, beta: float, resid=None, counts
     _call("ccvsq_finalize", _ptr(resid), _ptr(counts), _ptr(sq_err), _ptr(g_loss), K, D, float(M), float(N), float(beta),
                           _ptr(dE), _ptr(loss), _ptr(perp), _stream(dev))
     return dE, loss, perp
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-op composites: one FFI crossing per forward / backward
+# ------------------------------------------------------------------------------------------------
+def fast_stream_layout(lay: Layout) -> bool:
+    """Mirror of stream_fast_supported() for torch-allocated (16-byte aligned) tensors."""
+    D = lay.dim
+    if D % 4:
+        return False
+    if lay.S == 1:
+        return True
+    if lay.S % 4 or lay.C % 32:
+        return False
+    nslab = (lay.C + 255) // 256
+    return lay.C % nslab == 0 and (lay.C // nslab) % 32 == 0
+
+
+def uses_tensor_path(mode: str, K: int, D: int, N: int) -> bool:
+    return mode == "tensor" or (mode == "auto" and tensor_path_supported(K, D) and N >= 128 and K >= 64)
+
+
+@dataclass
+class ForwardOut:
+    idx: torch.Tensor                     # int64 [N]
+    zq: Optional[torch.Tensor]            # z's shape: fl(z + fl(E[idx] - z))
+    loss: Optional[torch.Tensor]          # 0-d fp32
+    perplexity: Optional[torch.Tensor]    # 0-d fp32
+    counts: Optional[torch.Tensor]        # int32 [K]
+
+
+def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: float, mode: str = "auto", n_cand: int = 4,
+                     margin_tau: float = 1.0, exact_fallback: bool = True, cb: Optional[PreparedCodebook] = None,
+                     indices_only: bool = False) -> ForwardOut:
+    """The whole forward of quantize.py:32-74 in one call of the C ABI (ccvsq_quantize_forward).
+    `cb` = cached codebook side data (frozen codebook); None rebuilds it inside the call."""
+    _req(z, torch.float32, "z")
+    w = _req(weight.detach(), torch.float32, "codebook")
+    if mode not in _lib.SEARCH_MODES:
+        raise ValueError(f"unknown search mode {mode!r}")
+    dev = z.device
+    K, D = w.shape
+    N = lay.rows
+    if lay.dim != D:
+        raise ValueError(f"latent dim {lay.dim} != codebook dim {D}")
+    m = _lib.SEARCH_MODES[mode]
+    tensor = uses_tensor_path(mode, K, D, N)
+    ws_bytes = int(_L.ccvsq_forward_workspace_bytes(N, K, D, m, n_cand, 0 if cb is not None else 1))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    hdr = torch.empty(_lib.HEADER_INTS + K, dtype=torch.int32, device=dev)
+    idx = torch.empty(N, dtype=torch.int64, device=dev)
+    zq = loss = perp = None
+    if not indices_only:
+        zq = torch.empty_like(z)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        perp = torch.empty((), dtype=torch.float32, device=dev)
+    a = _lib.ForwardArgs()
+    a.z, a.lay, a.E, a.K, a.beta = z.data_ptr(), lay, w.data_ptr(), K, float(beta)
+    a.search_mode, a.n_cand, a.margin_tau = m, int(n_cand), float(margin_tau)
+    a.exact_fallback, a.indices_only, a.prepare = int(exact_fallback), int(indices_only), 0
+    if cb is not None:
+        a.e_sq = cb.e_sq.data_ptr()
+        a.E_bf16 = cb.e_bf16.data_ptr() if cb.e_bf16 is not None else None
+        a.e_max = cb.e_max.data_ptr() if cb.e_max is not None else None
+    a.header, a.workspace, a.workspace_bytes = hdr.data_ptr(), ws.data_ptr(), ws_bytes
+    a.idx = idx.data_ptr()
+    if not indices_only:
+        a.zq, a.loss, a.perplexity = zq.data_ptr(), loss.data_ptr(), perp.data_ptr()
+    name = "ccvsq_screen" if tensor else "ccvsq_search_exact"
+    timed = PROFILER.timing is True or (PROFILER.timing and name in PROFILER.timing)
+    if timed:   # the dominant search kernel is bracketed by events recorded inside the C call
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        e.record()   # (instantiates the handles; re-recorded by the library around the kernel)
+        a.ev_search_begin, a.ev_search_end = s.cuda_event, e.cuda_event
+        PROFILER.records.append((name, s, e))
+    _call("ccvsq_quantize_forward", ctypes.byref(a), _stream(dev))
+    n = (1 if cb is None else 0) + ((2 + int(exact_fallback)) if tensor else 1)
+    if not indices_only:
+        n += 1 if fast_stream_layout(lay) else 2
+    PROFILER.launches += n
+    counts = None if indices_only else hdr[_lib.HEADER_INTS:]
+    return ForwardOut(idx, zq, loss, perp, counts)
+
+
+def quantize_backward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, idx: torch.Tensor,
+                      g_zq: Optional[torch.Tensor], g_loss: torch.Tensor, beta: float, want_dz: bool = True,
+                      want_dE: bool = True):
+    """Autograd backward of quantize.py:55-64 in one pass over z (ccvsq_quantize_backward):
+    dz = g_zq + (2 g/M)(z - E[idx]);  dE = -(2 beta g/M) sum_{idx=k}(z - E[k])."""
+    dev = z.device
+    K, D = weight.shape
+    dz = torch.empty_like(z) if want_dz else None
+    dE = torch.empty(K, D, dtype=torch.float32, device=dev) if want_dE else None   # doubles as the resid scratch
+    _call("ccvsq_quantize_backward", _ptr(z), lay, _ptr(weight), K, _ptr(idx), _ptr(g_zq), _ptr(g_loss), float(beta),
+          _ptr(dz), _ptr(dE), _ptr(dE), _stream(dev))
+    fused = fast_stream_layout(lay)
+    PROFILER.launches += (1 if fused or not (want_dz and want_dE) else 2) * int(want_dz or want_dE) + int(want_dE)
+    return dz, dE
 
 
 def ema_update(weight: torch.Tensor, n_ema: torch.Tensor, sum_ema: torch.Tensor, resid: torch.Tensor,

@@ -68,13 +68,9 @@ class _QuantizeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, weight, module):
         lay = ops.layout_of(z.shape, module.e_dim, module.mult)
-        cb = module._prepared()
-        idx = ops.search(z, lay, cb, module.search_mode, module.n_cand, module.margin_tau, module.exact_fallback)
-        zq, sq, counts = ops.assign(z, lay, weight, idx)
-        K, D = weight.shape
-        M, N = float(z.numel()), float(lay.rows)
-        _, loss, perp = ops.finalize(K, D, M, N, module.beta, counts=counts, sq_err=sq, want_loss=True,
-                                     want_perplexity=True)
+        out = ops.quantize_forward(z, lay, weight, module.beta, module.search_mode, module.n_cand, module.margin_tau,
+                                   module.exact_fallback, cb=module._cb_cached())
+        zq, loss, idx, perp, counts = out.zq, out.loss, out.idx, out.perplexity, out.counts
         ctx.lay = lay
         ctx.beta = module.beta
         # the EMA variant rewrites the codebook in place right after forward: keep the version the
@@ -91,15 +87,11 @@ class _QuantizeFn(torch.autograd.Function):
         if g_loss is None:
             g_loss = torch.zeros((), dtype=torch.float32, device=dev)
         g_loss = g_loss.to(torch.float32).contiguous()
-        dz = dE = None
-        if ctx.needs_input_grad[0]:
-            g = None if g_zq is None else g_zq.to(torch.float32).contiguous()
-            dz = ops.backward_dz(z, lay, weight, idx, g, g_loss)
-        if ctx.needs_input_grad[1]:
-            K, D = weight.shape
-            resid, _ = ops.code_stats(z, lay, weight, K, idx, sub=1.0, want_counts=False)
-            dE, _, _ = ops.finalize(K, D, float(z.numel()), float(lay.rows), ctx.beta, resid=resid, g_loss=g_loss,
-                                    want_dE=True)
+        want_dz, want_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (want_dz or want_dE):
+            return None, None, None
+        g = None if (g_zq is None or not want_dz) else g_zq.to(torch.float32).contiguous()
+        dz, dE = ops.quantize_backward(z, lay, weight, idx, g, g_loss, ctx.beta, want_dz, want_dE)
         return dz, dE, None
 
 
@@ -169,12 +161,16 @@ class VectorQuantizer(nn.Module):
     # which does not bump the autograd version counter, so no cheap staleness test exists.  The
     # rebuild is one pass over K*D floats (microseconds).  `freeze_codebook()` pins it for
     # inference loops over a fixed codebook.
-    def _prepared(self) -> ops.PreparedCodebook:
+    def _cb_cached(self) -> Optional[ops.PreparedCodebook]:
+        """The frozen side data if it still belongs to the live parameter, else None (= rebuild in-call)."""
         cb = self._cb
         w = self.embedding.weight
         if cb is not None and cb.ptr == w.data_ptr() and cb.weight.device == w.device:
             return cb
-        return ops.prepare_codebook(w)
+        return None
+
+    def _prepared(self) -> ops.PreparedCodebook:
+        return self._cb_cached() or ops.prepare_codebook(self.embedding.weight)
 
     def freeze_codebook(self):
         """Cache the codebook side data until `unfreeze_codebook()` (caller promises not to
@@ -226,8 +222,11 @@ class VectorQuantizer(nn.Module):
         if not z.is_cuda:
             raise RuntimeError("CUDA only; there is no CPU fallback")
         z = z.contiguous()
+        if z.dtype != torch.float32:
+            raise TypeError(f"the reference quantizer is FP32 end to end; got {z.dtype}")
         lay = ops.layout_of(z.shape, self.e_dim, self.mult)
-        return ops.search(z, lay, self._prepared(), self.search_mode, self.n_cand, self.margin_tau, self.exact_fallback)
+        return ops.quantize_forward(z, lay, self.embedding.weight, self.beta, self.search_mode, self.n_cand,
+                                    self.margin_tau, self.exact_fallback, cb=self._cb_cached(), indices_only=True).idx
 
     def embed_code(self, code, channel_major_hw=None):
         """E[code] (quantize.py:76-83).  `channel_major_hw=(h, w)` additionally fuses the caller's
@@ -291,7 +290,8 @@ class EMAVectorQuantizer(VectorQuantizer):
                 w = self.embedding.weight
                 lay = ops.layout_of(zc.shape, self.e_dim, self.mult)
                 idx = out[2][2].view(-1)
-                resid, counts = ops.code_stats(zc, lay, w, self.n_e, idx, sub=1.0)
+                resid, _ = ops.code_stats(zc, lay, w, self.n_e, idx, sub=1.0, want_counts=False)
+                counts = self.last_counts          # per-code usage from the forward's assign kernel
                 if self.sync:
                     sq = torch.zeros(1, dtype=torch.float64, device=zc.device)
                     resid, counts, _ = vq_dist.all_reduce_stats(resid, counts, sq)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CCVSQ_VERSION 101 /* major*100 + minor */
+#define CCVSQ_VERSION 102 /* major*100 + minor */
 
 typedef enum ccvsq_status {
   CCVSQ_OK = 0,
@@ -189,6 +189,69 @@ int ccvsq_finalize(const float* resid, const int32_t* counts, const double* sq_e
 int ccvsq_ema_update(float* E, float* n_ema, float* sum_ema, const float* resid,
                      const int32_t* counts, int K, int D, float decay, float eps, float* scratch,
                      void* stream);
+
+/* ---- whole-op entry points ---------------------------------------------------------------------
+ * ccvsq_quantize_forward enqueues the complete forward of the reference module
+ * (quantize.py:32-74: flatten, nearest code, gather, loss, straight-through value, perplexity) with
+ * ONE call: [prepare_codebook] -> screen -> rescore -> exact fallback (or the exact search) -> assign
+ * with the loss / perplexity finalisation folded into its last CTA.  The reference trainer calls the
+ * quantizer on 1k-5k latents at a time (scripts/bairhd/train_frame_autoencoder.sh:10,17-20): there the
+ * cost is host issue time, which this call keeps to one FFI crossing and one workspace.
+ *   header    [CCVSQ_HEADER_INTS + K] int32, caller-owned, ZEROED BY THE CALL; afterwards
+ *             header[CCVSQ_HEADER_INTS + k] = per-code usage counts (the rest is scratch)
+ *   workspace caller-owned scratch of ccvsq_forward_workspace_bytes(...) bytes (queue arrays and, when
+ *             e_sq == NULL, the codebook side data rebuilt on every call)
+ *   e_sq / E_bf16 / e_max : cached side data of ccvsq_prepare_codebook (all NULL = build per call);
+ *             prepare != 0 rebuilds the cached copy first
+ *   idx [N] int64 out; zq (z's layout, may be NULL); loss / perplexity device scalars (may be NULL)
+ *   indices_only != 0 stops after the search (QVidModel.encode keeps only info[2],
+ *             quantized_video_model.py:798-799)
+ *   ev_search_begin / ev_search_end : optional cudaEvent_t recorded around the dominant search kernel
+ *             (profiling hook used by bench.py's live roofline timing)                             */
+#define CCVSQ_HEADER_INTS 16
+#define CCVSQ_SEARCH_AUTO 0
+#define CCVSQ_SEARCH_TENSOR 1
+#define CCVSQ_SEARCH_EXACT 2
+
+typedef struct ccvsq_forward_args {
+  const float* z;
+  ccvsq_layout lay;
+  const float* E;
+  int32_t K;
+  float beta;
+  int32_t search_mode;
+  int32_t n_cand;
+  float margin_tau;
+  int32_t exact_fallback;
+  int32_t indices_only;
+  int32_t prepare;
+  float* e_sq;
+  void* E_bf16;
+  float* e_max;
+  int32_t* header;
+  void* workspace;
+  uint64_t workspace_bytes;
+  int64_t* idx;
+  float* zq;
+  float* loss;
+  float* perplexity;
+  void* ev_search_begin;
+  void* ev_search_end;
+} ccvsq_forward_args;
+
+uint64_t ccvsq_forward_workspace_bytes(int64_t N, int K, int D, int search_mode, int n_cand,
+                                       int with_codebook);
+int ccvsq_quantize_forward(const ccvsq_forward_args* args, void* stream);
+
+/* ccvsq_quantize_backward: the autograd backward of quantize.py:55-64 in one pass over z:
+ *   dz = g_zq + (2 g_loss / M)(z - E[idx])                       (dz may be NULL)
+ *   resid[k,:] = sum_{idx=k} (z - E[k])  (scratch [K, D], zeroed by the call; may be NULL)
+ *   dE = -(2 beta g_loss / M) resid                              (may be NULL; may alias resid)
+ * The per-code scatter-reduce rides on the same read of z as dz (vector reductions straight from
+ * registers) instead of a second pass.                                                          */
+int ccvsq_quantize_backward(const float* z, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
+                            const float* g_zq, const float* g_loss, float beta, float* dz, float* resid,
+                            float* dE, void* stream);
 
 #ifdef __cplusplus
 }

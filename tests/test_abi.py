@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_version():
-    assert _lib.load().ccvsq_version() == 101
+    assert _lib.load().ccvsq_version() == 102
 
 
 def test_argument_validation_without_gpu():
@@ -51,6 +51,34 @@ def test_argument_validation_without_gpu():
     assert lib.ccvsq_finalize(null, null, null, null, 4, 4, 0.0, 1.0, 0.25, null, null, null, null) == -1
 
 
+def test_composite_argument_validation_without_gpu():
+    lib = _lib.load()
+    null = ctypes.c_void_p(0)
+    assert lib.ccvsq_quantize_forward(None, null) == -5
+    a = _lib.ForwardArgs()
+    assert lib.ccvsq_quantize_forward(ctypes.byref(a), null) == -5            # z / E / header / idx missing
+    a.z = a.E = a.header = a.idx = 16
+    a.lay = _lib.Layout(4, 64, 16, 1)
+    a.K = 0
+    assert lib.ccvsq_quantize_forward(ctypes.byref(a), null) == -1            # K <= 0
+    a.K = 256
+    a.search_mode = 7
+    assert lib.ccvsq_quantize_forward(ctypes.byref(a), null) == -1            # unknown search mode
+    a.search_mode = 1
+    a.n_cand = 4
+    assert lib.ccvsq_quantize_forward(ctypes.byref(a), null) == -1            # workspace too small
+    assert b"workspace" in lib.ccvsq_last_error()
+    need = lib.ccvsq_forward_workspace_bytes(64, 256, 64, 1, 4, 1)
+    # e_sq + BF16 shadow (288 x 80 x 2) + queue arrays, 256-byte aligned sections
+    assert need >= 256 * 4 + 288 * 80 * 2 + 64 * 4 + 64 * 16 + 64 + 64 * 16
+    assert lib.ccvsq_forward_workspace_bytes(64, 256, 64, 2, 4, 0) == 256     # exact search, cached codebook: nothing
+    one = ctypes.c_void_p(16)
+    assert lib.ccvsq_quantize_backward(null, a.lay, one, 8, one, null, one, 0.25, one, null, null, null) == -5
+    assert lib.ccvsq_quantize_backward(one, a.lay, one, 8, one, null, one, 0.25, null, null, one, null) == -5   # dE without resid
+
+
 def test_layout_struct_matches_header():
+    assert ctypes.sizeof(_lib.ForwardArgs) == 168
+    assert _lib.ForwardArgs.lay.offset == 8 and _lib.ForwardArgs.e_sq.offset == 72 and _lib.ForwardArgs.idx.offset == 120
     assert ctypes.sizeof(_lib.Layout) == 24     # int64 + 3 x int32 (+4 pad)
     assert _lib.Layout.G.offset == 0 and _lib.Layout.C.offset == 8 and _lib.Layout.mult.offset == 16

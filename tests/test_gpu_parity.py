@@ -245,6 +245,89 @@ def test_assign_gather_backward_stats_finalize():
     torch.testing.assert_close(perp.cpu(), res.perplexity, rtol=1e-5, atol=0)
 
 
+# 128-bit fast paths (stream_fast.cu): partial last tile, two channel slabs, mult > 1, row-major rows,
+# S not a multiple of the 32-position tile; each against plain torch math on the CPU
+FAST_CASES = [((3, 256, 6, 6), 300, 256, 1), ((2, 512, 8, 8), 128, 512, 1), ((5, 256, 4, 4), 64, 128, 2),
+              ((70, 256), 100, 256, 1), ((3, 64, 2, 10), 50, 64, 1), ((2, 3, 128, 8, 8), 1024, 128, 1)]
+
+
+@pytest.mark.parametrize("shape,K,D,mult", FAST_CASES)
+def test_fast_stream_kernels(shape, K, D, mult):
+    z, cb = vq_oracle.synth(shape, K, D, "T", seed=17)
+    lay = ops.layout_of(shape, D, mult)
+    assert ops.fast_stream_layout(lay)
+    zl = vq_oracle.to_channel_last(z)
+    rows = zl.reshape(-1, D)
+    idx = vq_oracle.nearest(rows, cb)
+    zc, cbc, idc = z.to(DEV), cb.to(DEV), idx.to(DEV)
+    e = cb[idx]
+    N, M = rows.shape[0], z.numel()
+    back = (lambda r: vq_oracle.to_channel_first(r.view(zl.shape))) if len(shape) >= 4 else (lambda r: r.view(shape))
+
+    zq, sq, counts = ops.assign(zc, lay, cbc, idc)
+    assert torch.equal(zq.cpu(), back(rows + (e - rows)))
+    sq_ref = float(((e - rows).double() ** 2).sum())
+    assert abs(float(sq) - sq_ref) <= 1e-5 * sq_ref
+    assert torch.equal(counts.cpu(), torch.bincount(idx, minlength=K).to(torch.int32))
+
+    out, err = ops.gather(idc, cbc)
+    assert int(err) == 0 and torch.equal(out.cpu(), e)
+    if lay.S > 1:
+        out_cm, _ = ops.gather(idc, cbc, lay)
+        assert torch.equal(out_cm.view(shape).cpu(), back(e))
+    bad = idc.clone()
+    bad[N // 2] = -3
+    _, err = ops.gather(bad, cbc, lay if lay.S > 1 else None)
+    assert int(err) == 1
+
+    torch.manual_seed(5)
+    g_zq, g_loss = torch.randn(shape), torch.tensor(0.37)
+    dz_rows = 2 * 0.37 * (rows - e) / M
+    resid_ref = torch.zeros(K, D, dtype=torch.float64).index_add_(0, idx, (rows - e).double()).float()
+    dz, dE = ops.quantize_backward(zc, lay, cbc, idc, g_zq.to(DEV), g_loss.to(DEV), 0.25)
+    torch.testing.assert_close(dz.cpu(), back(dz_rows) + g_zq, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(dE.cpu(), -(2 * 0.25 * 0.37 / M) * resid_ref, rtol=1e-4, atol=1e-8)
+    dz0, none = ops.quantize_backward(zc, lay, cbc, idc, None, g_loss.to(DEV), 0.25, want_dE=False)
+    assert none is None
+    torch.testing.assert_close(dz0.cpu(), back(dz_rows), rtol=1e-5, atol=1e-7)
+    none, dE1 = ops.quantize_backward(zc, lay, cbc, idc, None, g_loss.to(DEV), 0.25, want_dz=False)
+    assert none is None
+    torch.testing.assert_close(dE1.cpu(), dE.cpu(), rtol=1e-4, atol=1e-8)
+    torch.testing.assert_close(ops.backward_dz(zc, lay, cbc, idc, g_zq.to(DEV), g_loss.to(DEV)).cpu(), dz.cpu(), rtol=0, atol=0)
+
+    resid, cnt = ops.code_stats(zc, lay, cbc, K, idc, sub=1.0)
+    torch.testing.assert_close(resid.cpu(), resid_ref, rtol=1e-4, atol=1e-5)
+    assert torch.equal(cnt.cpu(), counts.cpu())
+    sums, _ = ops.code_stats(zc, lay, None, K, idc, sub=0.0, want_counts=False)
+    sums_ref = torch.zeros(K, D, dtype=torch.float64).index_add_(0, idx, rows.double()).float()
+    torch.testing.assert_close(sums.cpu(), sums_ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape,K,D,mult,mode", [((16, 256, 16, 16), 1024, 256, 1, "auto"), ((3, 64, 5, 7), 200, 64, 1, "exact"),
+                                                  ((5, 256, 4, 4), 64, 128, 2, "tensor"), ((4, 16, 2), 128, 1, 1, "auto"),
+                                                  ((300, 64), 96, 64, 1, "auto")])
+def test_composite_forward_equals_stepwise(shape, K, D, mult, mode):
+    """ccvsq_quantize_forward (one call, folded finalize, in-call codebook side data) against the
+    step-by-step entry points, and with a cached (frozen) codebook."""
+    z, cb = vq_oracle.synth(shape, K, D, "T" if D > 1 else "I", seed=23)
+    if D == 1:
+        cb = torch.rand(K, 1)
+    zc, cbc = z.to(DEV), cb.to(DEV)
+    lay = ops.layout_of(shape, D, mult)
+    pcb = ops.prepare_codebook(cbc)
+    idx = ops.search(zc, lay, pcb, mode=mode)
+    zq, sq, counts = ops.assign(zc, lay, cbc, idx)
+    _, loss, perp = ops.finalize(K, D, float(z.numel()), float(lay.rows), 0.25, counts=counts, sq_err=sq, want_loss=True,
+                                 want_perplexity=True)
+    for cached in (None, pcb):
+        out = ops.quantize_forward(zc, lay, cbc, 0.25, mode, cb=cached)
+        assert torch.equal(out.idx, idx) and torch.equal(out.zq, zq) and torch.equal(out.counts, counts)
+        torch.testing.assert_close(out.loss, loss, rtol=1e-6, atol=0)
+        torch.testing.assert_close(out.perplexity, perp, rtol=1e-6, atol=0)
+        only = ops.quantize_forward(zc, lay, cbc, 0.25, mode, cb=cached, indices_only=True)
+        assert torch.equal(only.idx, idx) and only.zq is None
+
+
 def test_mult_and_flat_layouts_through_abi():
     # mult > 1 on a channel-major tensor, and the ndim < 4 contiguous-row case incl. e_dim = 1
     for shape, K, D, mult in [((3, 32, 4, 5), 64, 8, 4), ((50, 24), 16, 24, 1), ((4, 16, 2), 128, 1, 1)]:
