@@ -38,6 +38,7 @@ WORKLOADS = {
     "c1": ((1, 16), 256, 16, 16, 1024, "BAIR-256 quantizer forward, 16 frames x 16x16 latents, K=1024, D=256"),
     "c2": ((64, 16), 256, 16, 16, 1024, "BAIR-256 encode+decode, 64 clips x 16 frames x 16x16 latents, K=1024, D=256"),
     "c3": ((128, 16), 256, 8, 8, 16384, "Kinetics-600 64p shard, 128 clips x 16 frames x 8x8 latents, K=16384, D=256"),
+    "c3d512": ((64, 16), 512, 8, 8, 16384, "Kinetics-600 shard at the reference script's D=512 (SURVEY F7), 64 clips x 16 frames x 8x8, K=16384"),
     "c4": ((2048, 16), 256, 8, 8, 16384, "large-codebook stress shard, 2^21 latents, K=16384, D=256"),
     "train": ((64, 16), 256, 16, 16, 1024, "training-mode quantizer (fwd+bwd+EMA update), c2 shape"),
 }
@@ -250,7 +251,8 @@ def main():
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        step(z)
+        out = step(z)      # (same object lifetime pattern as the timed loop: the caching allocator reaches
+                           #  its steady state here, not inside the timed region)
     barrier()
     # timed region: CUDA events on the launching stream; the dominant kernel (screen) is additionally
     # bracketed by its own events so its launch duration is measured live inside the same region

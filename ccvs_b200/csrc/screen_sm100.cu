@@ -27,10 +27,12 @@
 //   warp 0      TMA producer (both CTAs, each loads its half of every B tile)
 //   warp 1      MMA issuer (leader CTA of the pair only)
 //   warp 2      TMEM allocator
+//   warp 3      L2 prefetcher for the latents (one row tile ahead of the A loaders)
 //   warps 4-7   epilogue: tcgen05.ld 32 columns at a time, max tree, candidate list, outputs
 //   warps 8-15  A loaders: global FP32 -> BF16 -> tcgen05.st, row norms for the margin
 #include <cuda.h>
 #include <float.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ccvsq {
@@ -240,7 +242,9 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // kernel configuration
 // ------------------------------------------------------------------------------------------------
 constexpr int BM = 128;              // latent rows per CTA (TMEM lanes)
-constexpr int BN = SCREEN_BN;        // codes per accumulator tile (UMMA N)
+// codes per accumulator tile (UMMA N) is a template parameter: 96 (long sweeps: fewest per-tile hand-offs)
+// or 64 (three accumulators AND two A buffers fit the 512 tensor-memory columns up to D = 256, and three
+// accumulators fit beside a D = 512 A buffer)
 constexpr int LCAP = 16;             // candidate-list entries (groups of 4 codes) per row
 constexpr int LKEEP = LCAP - 8;      // one slow path appends up to 8 groups: compact down to this many first
 constexpr uint32_t SC_STRIDE = BM * 16;   // entry e of a row: 4 raw scores at sc_base + e*SC_STRIDE ...
@@ -258,9 +262,9 @@ struct ScreenSmem {
   uint32_t block_bytes, ext_off, slot_bytes, slot_tx;
   int nslots;
 };
-__host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg) {
+__host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg, int bn) {
   ScreenSmem s;
-  const uint32_t rows = BN / cg;                    // codes of a tile held by one CTA
+  const uint32_t rows = bn / cg;                    // codes of a tile held by one CTA
   s.block_bytes = rows * 128;                       // one 64-dim block, 128B-swizzled
   s.ext_off = dblk * s.block_bytes;                 // bias extension: [2 K-chunks][rows][16 B]
   s.slot_tx = s.ext_off + rows * 32;
@@ -438,14 +442,14 @@ __device__ __forceinline__ void load_chunk(float (&v)[32], const float* __restri
   }
 }
 
-template <int CG, bool DBG>
+template <int CG, bool DBG, int BN>
 __global__ void __launch_bounds__(SCREEN_THREADS, 1)
 screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_ext,
               const float* __restrict__ z, const Lay L, const float* __restrict__ e_max, float margin_scale,
               int K_pad, int n_tiles, int dblk, int nacc, int abuf_n, int n_cand, int num_group_tiles,
               const ScreenOut out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const ScreenSmem lay = screen_smem_layout(dblk, CG);
+  const ScreenSmem lay = screen_smem_layout(dblk, CG, BN);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -563,6 +567,34 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           __syncwarp();
           if (++slot == nslots) { slot = 0; phase ^= 1; }
           if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // =========================== L2 prefetcher ===================================================
+    // The A loaders are latency-bound (one latent row per lane, 32 loads in flight per lane): on short
+    // code sweeps (K = 1024) a 128 KiB row tile per CTA has to arrive within one sweep.  This warp runs
+    // one row tile ahead of them and pulls the tile after next into L2 (fire-and-forget prefetches, no
+    // registers or shared memory), so the loaders' global loads become L2 hits.
+    uint32_t tl = 0;
+    for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
+      const int gn = gt + num_groups;                     // the tile the loaders take after this one
+      if (gn >= num_group_tiles) break;
+      const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
+      mbar_wait_sleep(a_empty(ab), a_phase ^ 1);          // the loaders are starting on tile gt now
+      const int64_t n0 = ((int64_t)gn * CG + rank) * BM;
+      if (n0 >= L.N) break;
+      const int64_t n1 = (n0 + BM < L.N ? n0 + BM : L.N) - 1;
+      if (L.S == 1) {                                     // contiguous rows
+        const char* base = reinterpret_cast<const char*>(z + n0 * L.D);
+        const int64_t bytes = (n1 - n0 + 1) * (int64_t)L.D * 4;
+        for (int64_t off = (int64_t)lane * 128; off < bytes; off += 32 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+      } else {                                            // 32 consecutive positions of a channel share a line
+        const int64_t pos_lo = n0 / L.mult, pos_hi = n1 / L.mult;
+        for (int64_t pg = pos_lo; pg <= pos_hi; pg += 32) {
+          const float* pz = z + pos_base(L, pg);
+          for (int c = lane; c < L.C; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + (int64_t)c * L.S));
         }
       }
     }
@@ -703,23 +735,25 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           }
         };
 
-        // three 32-column chunks; the tcgen05.ld of the next chunk overlaps the max tree of this one,
-        // and the accumulator is handed back as soon as the last chunk is in registers
+        // BN/32 chunks of 32 columns; the tcgen05.ld of the next chunk overlaps the max tree of this
+        // one, and the accumulator is handed back as soon as the last chunk is in registers
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr0, ra);
         tmem_ld_wait();
         tmem_ld32(taddr0 + 32, rb);
         process(ra, 0);
         tmem_ld_wait();
-        tmem_ld32(taddr0 + 64, ra);
-        process(rb, 32);
-        tmem_ld_wait();
+        if constexpr (BN == 96) {
+          tmem_ld32(taddr0 + 64, ra);
+          process(rb, 32);
+          tmem_ld_wait();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
         }
-        process(ra, 64);
+        if constexpr (BN == 96) process(ra, 64); else process(rb, 32);
         if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
       }
 
@@ -772,19 +806,20 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int64
   return CCVSQ_OK;
 }
 
-template <int CG>
+template <int CG, int BN>
 static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const float* e_max,
-                         float margin_scale, int K_pad, int D, int n_cand, const ScreenOut& out,
-                         cudaStream_t st) {
+                         float margin_scale, int K, int K_pad, int D, int n_cand, int nacc, int abuf,
+                         const ScreenOut& out, cudaStream_t st) {
+  static_assert(BN == 96 || BN == 64, "epilogue is written for 2 or 3 chunks of 32 columns");
   const int dblk = D / 64;
-  const ScreenSmem lay = screen_smem_layout(dblk, CG);
+  const ScreenSmem lay = screen_smem_layout(dblk, CG, BN);
   CCVSQ_REQUIRE(lay.nslots >= 1, CCVSQ_UNSUPPORTED, "screen: D=%d leaves room for %d B slots", D, lay.nslots);
   EncodeTiledFn enc;
   if (int rc = get_encode_fn(&enc)) return rc;
   CUtensorMap mb, mx;
   if (int rc = make_map(enc, &mb, E_bf16, K_pad, D + SCREEN_EXT, 64, BN / CG, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_map(enc, &mx, E_bf16, K_pad, D + SCREEN_EXT, 8, BN / CG, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-  auto kern = out.dbg_cand ? screen_kernel<CG, true> : screen_kernel<CG, false>;
+  auto kern = out.dbg_cand ? screen_kernel<CG, true, BN> : screen_kernel<CG, false, BN>;
   if (int rc = enable_smem(kern, lay.total)) return rc;
   const int64_t rows_per_group = (int64_t)BM * CG;
   const int64_t group_tiles = (L.N + rows_per_group - 1) / rows_per_group;
@@ -804,20 +839,33 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // Tensor-memory budget (512 columns): nacc accumulators of BN, 8 columns of bias extension, abuf A
-  // buffers of D/2.  Long code sweeps prefer a third accumulator (the MMA -> epilogue -> MMA chain
-  // per accumulator is longer than two tile times) over a second A buffer (one bubble per sweep);
-  // short sweeps prefer streaming the next A tile under the MMAs.
-  const int n_tiles = K_pad / BN;
-  const int a_cols = D / 2;
-  int abuf = (2 * a_cols + 8 + 2 * BN <= (int)TMEM_COLS) ? 2 : 1;
-  if (abuf == 2 && n_tiles >= 24 && (2 * a_cols + 8 + 3 * BN > (int)TMEM_COLS)) abuf = 1;
-  int nacc = ((int)TMEM_COLS - 8 - abuf * a_cols) / BN;
-  if (nacc > 3) nacc = 3;
-  CCVSQ_REQUIRE(nacc >= 2, CCVSQ_UNSUPPORTED, "screen: D=%d leaves %d accumulators", D, nacc);
+  const int n_tiles = (K + BN - 1) / BN;          // rows [K, n_tiles*BN) of the shadow are padding (bias -3e38)
+  CCVSQ_REQUIRE(n_tiles * BN <= K_pad, CCVSQ_BAD_SHAPE, "screen: codebook shadow has %d rows, the sweep needs %d",
+                K_pad, n_tiles * BN);
   CCVSQ_CUDA(cudaLaunchKernelEx(&cfg, kern, mb, mx, z, L, e_max, margin_scale, K_pad, n_tiles, dblk, nacc, abuf,
                                 n_cand, (int)group_tiles, out));
   return CCVSQ_OK;
+}
+
+// Tensor-memory budget (512 columns): nacc accumulators of BN columns, 8 columns of bias extension,
+// abuf A buffers of D/2.  The MMA -> commit -> epilogue -> arrive -> MMA chain of one accumulator is longer
+// than two tile times, so three accumulators come first.  Long code sweeps then prefer the wider tile
+// (fewer hand-offs per code) over a second A buffer (one bubble per sweep); short sweeps prefer streaming
+// the next A tile under the MMAs, which at D = 256 only fits with 64-column accumulators.
+struct ScreenPlan { int bn, nacc, abuf; };
+static ScreenPlan plan_screen(int K, int D) {
+  const int a_cols = D / 2;
+  auto fits = [&](int bn, int nacc, int abuf) { return nacc * bn + 8 + abuf * a_cols <= (int)TMEM_COLS; };
+  static const int forced_bn = [] { const char* e = getenv("CCVSQ_SCREEN_BN"); return e ? atoi(e) : 0; }();
+  const bool long_sweep = (K + 95) / 96 >= 24;
+  ScreenPlan best = {96, 2, 1};
+  const ScreenPlan order_long[] = {{96, 3, 2}, {96, 3, 1}, {64, 3, 2}, {64, 3, 1}, {96, 2, 2}, {96, 2, 1}};
+  const ScreenPlan order_short[] = {{96, 3, 2}, {64, 3, 2}, {96, 3, 1}, {64, 3, 1}, {96, 2, 2}, {96, 2, 1}};
+  for (const ScreenPlan& p : long_sweep ? order_long : order_short) {
+    if (forced_bn && p.bn != forced_bn) continue;
+    if (fits(p.bn, p.nacc, p.abuf)) { best = p; break; }
+  }
+  return best;
 }
 
 }  // namespace ccvsq
@@ -840,12 +888,23 @@ static int screen_impl(const float* z, ccvsq_layout lay, const void* E_bf16, con
   CCVSQ_REQUIRE(cta_group == 1 || cta_group == 2, CCVSQ_BAD_SHAPE, "screen: cta_group=%d", cta_group);
   const int K_pad = ccvsq_codebook_rows(K);
   const float margin_scale = margin_tau * 0.00390625f;   // tau * 2^-8
-  if (cta_group == 2)
-    return launch_screen<2>(E_bf16, z, L, e_max, margin_scale, K_pad, D, n_cand, out, (cudaStream_t)stream);
-  return launch_screen<1>(E_bf16, z, L, e_max, margin_scale, K_pad, D, n_cand, out, (cudaStream_t)stream);
+  const ScreenPlan pl = plan_screen(K, D);
+  CCVSQ_REQUIRE(pl.nacc * pl.bn + 8 + pl.abuf * (D / 2) <= (int)TMEM_COLS, CCVSQ_UNSUPPORTED,
+                "screen: D=%d does not fit the tensor-memory budget", D);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cta_group == 2) {
+    if (pl.bn == 64) return launch_screen<2, 64>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
+    return launch_screen<2, 96>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
+  }
+  if (pl.bn == 64) return launch_screen<1, 64>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
+  return launch_screen<1, 96>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
 }
 
-extern "C" int ccvsq_codebook_rows(int K) { return (K + SCREEN_BN - 1) / SCREEN_BN * SCREEN_BN; }
+// rows of the BF16 codebook shadow: enough for a sweep with either tile width
+extern "C" int ccvsq_codebook_rows(int K) {
+  const int a = (K + 95) / 96 * 96, b = (K + 63) / 64 * 64;
+  return a > b ? a : b;
+}
 
 extern "C" int ccvsq_screen(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
                             float margin_tau, int n_cand, int64_t* idx, int32_t* queue_count,

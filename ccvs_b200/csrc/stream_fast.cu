@@ -65,7 +65,7 @@ __device__ void fold_finalize(const StreamArgs& a, unsigned total_ctas, bool* s_
 // channel-major tiles
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int MAXIT>
-__global__ void __launch_bounds__(FNT) cm4_kernel(const StreamArgs a, const Lay L, const int CS) {
+__global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : 4) cm4_kernel(const StreamArgs a, const Lay L, const int CS) {
   extern __shared__ float4 tile4[];                 // [FPT][CS/4], chunk index ^ (position/4)
   __shared__ float s_red[FNT / 32];
   __shared__ bool s_last;
@@ -79,10 +79,19 @@ __global__ void __launch_bounds__(FNT) cm4_kernel(const StreamArgs a, const Lay 
   const bool has_g = MODE == MODE_BACKWARD && a.g != nullptr;
   const bool need_e = MODE != MODE_STATS || a.sub != 0.f;
 
-  // ---- streaming loads first (independent of the gather below)
+  // ---- streaming loads first (independent of the gather below).  Addressing avoids per-thread 64-bit
+  // divisions: with S % 32 == 0 a tile lies inside one group g, so (g, s0) is one 32-bit division per CTA.
   float xa[MAXIT][4][4], ga[MAXIT][4][4];           // [it][channel j][position i]
   int64_t base[MAXIT];
   bool valid[MAXIT];
+  const bool tile_in_group = (L.S & 31) == 0;
+  int64_t tile_base = 0;
+  if (tile_in_group) {
+    const uint32_t tpg = (uint32_t)L.S >> 5;        // tiles per group
+    const uint32_t g = blockIdx.x / tpg;
+    const uint32_t s0 = (blockIdx.x - g * tpg) << 5;
+    tile_base = ((int64_t)g * L.C + c_lo) * L.S + s0;
+  }
 #pragma unroll
   for (int it = 0; it < MAXIT; ++it) {
     const int b = tid + it * FNT;
@@ -90,10 +99,14 @@ __global__ void __launch_bounds__(FNT) cm4_kernel(const StreamArgs a, const Lay 
     valid[it] = b < nblk && 4 * p4 < np;
     base[it] = 0;
     if (valid[it]) {
-      const int64_t pos = p0 + 4 * p4;
-      const int64_t g = pos / L.S;
-      const int s = (int)(pos - g * L.S);
-      base[it] = (g * L.C + c_lo + 4 * cq) * (int64_t)L.S + s;
+      if (tile_in_group) {
+        base[it] = tile_base + (int64_t)(4 * cq) * L.S + 4 * p4;
+      } else {
+        const int64_t pos = p0 + 4 * p4;
+        const int64_t g = pos / L.S;
+        const int s = (int)(pos - g * L.S);
+        base[it] = (g * L.C + c_lo + 4 * cq) * (int64_t)L.S + s;
+      }
       if (HAS_X) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -107,20 +120,32 @@ __global__ void __launch_bounds__(FNT) cm4_kernel(const StreamArgs a, const Lay 
     }
   }
 
-  // ---- gather the codebook rows of this tile into shared memory
+  // ---- gather the codebook rows of this tile into shared memory: one warp per position, lanes over
+  // the 16-byte chunks of the row (QS <= 64: at most two per lane)
   if (need_e) {
-    const int total = np * QS;
-    for (int i = tid; i < total; i += FNT) {
-      const int p = i / QS, q = i - p * QS;
-      const int c = c_lo + 4 * q;
-      const int m = c / L.D, j = c - m * L.D;
-      int64_t k = __ldg(a.idx + (p0 + p) * L.mult + m);
-      if (k < 0 || k >= a.K) {
-        if (MODE == MODE_GATHER && a.err_flag) atomicOr(a.err_flag, 1);
-        k = k < 0 ? 0 : a.K - 1;
-        if (MODE == MODE_GATHER) k = 0;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int p = warp; p < np; p += FNT / 32) {
+      const int sw = (p >> 2) & 7;
+      if (L.mult == 1) {
+        int64_t k = __ldg(a.idx + p0 + p);
+        if (k < 0 || k >= a.K) {
+          if (MODE == MODE_GATHER) { if (a.err_flag && lane == 0) atomicOr(a.err_flag, 1); k = 0; }
+          else k = k < 0 ? 0 : a.K - 1;
+        }
+        const float4* src = reinterpret_cast<const float4*>(a.E + (size_t)k * L.D + c_lo);
+        for (int q = lane; q < QS; q += 32) tile4[p * QS + (q ^ sw)] = __ldg(src + q);
+      } else {
+        for (int q = lane; q < QS; q += 32) {
+          const int c = c_lo + 4 * q;
+          const int m = c / L.D, j = c - m * L.D;
+          int64_t k = __ldg(a.idx + (p0 + p) * L.mult + m);
+          if (k < 0 || k >= a.K) {
+            if (MODE == MODE_GATHER) { if (a.err_flag) atomicOr(a.err_flag, 1); k = 0; }
+            else k = k < 0 ? 0 : a.K - 1;
+          }
+          tile4[p * QS + (q ^ sw)] = __ldg(reinterpret_cast<const float4*>(a.E + (size_t)k * L.D + j));
+        }
       }
-      tile4[p * QS + (q ^ ((p >> 2) & 7))] = __ldg(reinterpret_cast<const float4*>(a.E + (size_t)k * L.D + j));
     }
   }
   if (a.counts && blockIdx.y == 0 && (MODE == MODE_ASSIGN || MODE == MODE_STATS)) {
@@ -180,7 +205,8 @@ __global__ void __launch_bounds__(FNT) cm4_kernel(const StreamArgs a, const Lay 
     }
     if ((MODE == MODE_STATS || MODE == MODE_BACKWARD) && a.resid) {
       const int c = c_lo + 4 * cq;
-      const int m = c / L.D, j0 = c - m * L.D;
+      const int m = L.mult == 1 ? 0 : c / L.D;
+      const int j0 = c - m * L.D;
       const float sub = MODE == MODE_BACKWARD ? 1.f : a.sub;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -308,6 +334,94 @@ __global__ void __launch_bounds__(FNT) rows4_kernel(const StreamArgs a, const in
   if (MODE == MODE_ASSIGN && a.fin.ticket) fold_finalize(a, gridDim.x, &s_last, s_red);
 }
 
+// Row-major, D % 128 == 0: one warp per RPW consecutive rows, lanes over the chunks of a row.  No
+// divisions or per-chunk index arithmetic: ~8 (gather) to ~25 (assign) instructions per 16 bytes.
+template <int MODE>
+__global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kernel(const StreamArgs a, const int64_t N, const int D) {
+  __shared__ float s_red[FNT / 32];
+  __shared__ bool s_last;
+  constexpr int RPW = 4;
+  const int lane = threadIdx.x & 31;
+  const int Q = D >> 2, QL = D >> 7;                        // chunks per row / per lane
+  const int64_t n_base = ((int64_t)blockIdx.x * (FNT / 32) + (threadIdx.x >> 5)) * RPW;
+  const bool has_g = MODE == MODE_BACKWARD && a.g != nullptr;
+  const bool need_e = MODE != MODE_STATS || a.sub != 0.f;
+  int64_t k[RPW];
+  bool valid[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int64_t n = n_base + i;
+    valid[i] = n < N;
+    int64_t kk = valid[i] ? __ldg(a.idx + n) : 0;
+    if (kk < 0 || kk >= a.K) {
+      if (MODE == MODE_GATHER) { if (a.err_flag && lane == 0) atomicOr(a.err_flag, 1); kk = 0; }
+      else if (MODE == MODE_STATS) { valid[i] = false; kk = 0; }
+      else kk = kk < 0 ? 0 : a.K - 1;
+    }
+    k[i] = kk;
+    if (a.counts && valid[i] && lane == 0 && (MODE == MODE_ASSIGN || MODE == MODE_STATS)) atomicAdd(a.counts + kk, 1);
+  }
+  float coef = 0.f;
+  if (MODE == MODE_BACKWARD) coef = __ldg(a.g_loss) * a.coef_scale;
+  float acc = 0.f;
+  for (int c = 0; c < QL; ++c) {
+    const int j = lane + 32 * c;
+    float4 xv[RPW], gv[RPW], ev[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      if (!valid[i]) continue;
+      if (MODE != MODE_GATHER) xv[i] = __ldcs(reinterpret_cast<const float4*>(a.x) + (n_base + i) * Q + j);
+      if (has_g) gv[i] = __ldcs(reinterpret_cast<const float4*>(a.g) + (n_base + i) * Q + j);
+      if (need_e) ev[i] = __ldg(reinterpret_cast<const float4*>(a.E) + (size_t)k[i] * Q + j);
+    }
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      if (!valid[i]) continue;
+      float x[4], e[4], g[4], out[4];
+      if (MODE != MODE_GATHER) *reinterpret_cast<float4*>(x) = xv[i];
+      if (need_e) *reinterpret_cast<float4*>(e) = ev[i];
+      if (has_g) *reinterpret_cast<float4*>(g) = gv[i];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (MODE == MODE_ASSIGN) {
+          const float diff = __fsub_rn(e[t], x[t]);
+          out[t] = __fadd_rn(x[t], diff);
+          acc = fmaf(diff, diff, acc);
+        } else if (MODE == MODE_BACKWARD) {
+          const float v = __fmul_rn(coef, __fsub_rn(x[t], e[t]));
+          out[t] = has_g ? __fadd_rn(v, g[t]) : v;
+        } else if (MODE == MODE_GATHER) {
+          out[t] = e[t];
+        }
+      }
+      if (MODE != MODE_STATS && a.out) {
+        float4* dst = reinterpret_cast<float4*>(a.out) + (n_base + i) * Q + j;
+        const float4 v = *reinterpret_cast<const float4*>(out);
+        if (MODE == MODE_GATHER) __stcs(dst, v); else *dst = v;
+      }
+      if ((MODE == MODE_STATS || MODE == MODE_BACKWARD) && a.resid) {
+        const float sub = MODE == MODE_BACKWARD ? 1.f : a.sub;
+        float r[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) r[t] = need_e ? x[t] - sub * e[t] : x[t];
+        red_add_v4(a.resid + ((size_t)k[i] * Q + j) * 4, r[0], r[1], r[2], r[3]);
+      }
+    }
+  }
+  if (MODE == MODE_ASSIGN && a.sq_err) {
+    acc = warp_sum(acc);
+    if (lane == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < FNT / 32; ++w) s += s_red[w];
+      atomicAdd(a.sq_err, (double)s);
+    }
+  }
+  if (MODE == MODE_ASSIGN && a.fin.ticket) fold_finalize(a, gridDim.x, &s_last, s_red);
+}
+
 // ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
@@ -341,6 +455,13 @@ static int launch_cm4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
 
 template <int MODE>
 static int launch_rows4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
+  if (L.D % 128 == 0) {
+    const int64_t blocks = (L.N + 4 * (FNT / 32) - 1) / (4 * (FNT / 32));
+    CCVSQ_REQUIRE(blocks < (1ll << 31), CCVSQ_BAD_SHAPE, "stream kernel: %lld CTAs exceed the grid limit", (long long)blocks);
+    rowsw_kernel<MODE><<<(unsigned)blocks, FNT, 0, st>>>(a, L.N, L.D);
+    CCVSQ_LAUNCH_CHECK();
+    return CCVSQ_OK;
+  }
   const int64_t total = L.N * (L.D >> 2);
   const int64_t blocks = (total + 4 * FNT - 1) / (4 * FNT);
   CCVSQ_REQUIRE(blocks < (1ll << 31), CCVSQ_BAD_SHAPE, "stream kernel: %lld CTAs exceed the grid limit", (long long)blocks);

@@ -71,7 +71,7 @@ const char* ccvsq_last_error(void); /* thread-local, valid until the next failin
  *            multiplies the 16 extra columns with a constant (1,1,1,0,...) block, so the bias is
  *            added by the tensor core itself.
  *   e_max    [1]     fp32   out (may be NULL): max_k ||e_k||                                   */
-int ccvsq_codebook_rows(int K); /* K rounded up to the screen's code tile (96) */
+int ccvsq_codebook_rows(int K); /* K rounded up so that a sweep with either screen tile width (96 / 64) fits */
 int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf16, float* e_max,
                            void* stream);
 

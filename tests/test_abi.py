@@ -47,7 +47,7 @@ def test_argument_validation_without_gpu():
     assert lib.ccvsq_screen(one, good, one, one, 256, 1.0, 9, one, one, one, one, one, null) == -1   # n_cand > 8
     assert lib.ccvsq_screen(ctypes.c_void_p(8), good, one, one, 256, 1.0, 4, one, one, one, one, one, null) == -3  # MISALIGNED
     assert lib.ccvsq_screen(one, good, one, one, 256, 1.0, 4, null, one, one, one, one, null) == -5  # NULL_POINTER
-    assert lib.ccvsq_codebook_rows(1024) == 1056 and lib.ccvsq_codebook_rows(96) == 96
+    assert lib.ccvsq_codebook_rows(1024) == 1056 and lib.ccvsq_codebook_rows(96) == 128 and lib.ccvsq_codebook_rows(192) == 192
     assert lib.ccvsq_finalize(null, null, null, null, 4, 4, 0.0, 1.0, 0.25, null, null, null, null) == -1
 
 
