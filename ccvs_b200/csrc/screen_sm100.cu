@@ -96,12 +96,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();   // ~2 s
   }
 }
-// Long waits (a whole code sweep): back off so the spin does not take issue slots from working warps.
+// Long waits (a whole code sweep): let the hardware suspend the thread (try_wait with a suspend-time hint wakes
+// on the phase flip) instead of polling: a nanosleep poll loop cost a quarter of all issued instructions of the
+// kernel at K = 1024, taken from the schedulers the epilogue warps run on.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(256);
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
@@ -247,9 +261,14 @@ constexpr int BM = 128;              // latent rows per CTA (TMEM lanes)
 // accumulators fit beside a D = 512 A buffer)
 constexpr int LCAP = 16;             // candidate-list entries (groups of 4 codes) per row
 constexpr int LKEEP = LCAP - 8;      // one slow path appends up to 8 groups: compact down to this many first
-constexpr uint32_t SC_STRIDE = BM * 16;   // entry e of a row: 4 raw scores at sc_base + e*SC_STRIDE ...
-constexpr uint32_t CO_STRIDE = BM * 4;    // ... and the first code of the group at co_base + e*CO_STRIDE
-constexpr uint32_t LIST_BYTES = LCAP * (SC_STRIDE + CO_STRIDE);
+// candidate list in shared memory: entry e of a row = 4 raw scores at sc_base + e*ENT_STRIDE (sc_base = list +
+// row*16) and the first code of the group at co_base + e*ENT_STRIDE (co_base = list + BM*16 + row*4): ONE stride
+// for both halves, so an append computes a single address per group
+constexpr uint32_t ENT_STRIDE = BM * 16 + BM * 4;
+constexpr uint32_t SC_STRIDE = ENT_STRIDE;
+constexpr uint32_t CO_STRIDE = ENT_STRIDE;
+constexpr uint32_t CO_OFFSET = BM * 16;
+constexpr uint32_t LIST_BYTES = LCAP * ENT_STRIDE;
 constexpr int SCREEN_THREADS = 512;
 constexpr int MAX_SLOTS = 8;
 // tensor-memory columns (32-bit): two accumulators, the constant bias-extension A block, A buffers
@@ -664,7 +683,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
     const uint32_t sc_base = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
-    const uint32_t co_base = smem_base + lay.list + LCAP * SC_STRIDE + (uint32_t)row_in_tile * 4u;
+    const uint32_t co_base = smem_base + lay.list + CO_OFFSET + (uint32_t)row_in_tile * 4u;
     const uint32_t drop_addr = smem_base + lay.drop + (uint32_t)row_in_tile * 4u;
     const uint32_t te_bar = (CG == 1) ? tmem_empty(0) : mapa(tmem_empty(0), 0);
     const float emax = e_max ? __ldg(e_max) : 1.f;
@@ -687,10 +706,12 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
         const int col0 = j * BN;
 
-        // One 32-column chunk of this thread's row.  Fast path: a 16-instruction 3-input max tree.  A
-        // chunk can only contribute candidates if its maximum reaches (running max - margin); then
-        // (slow path, ~1 chunk in 5 per warp) the threshold is refreshed and every group of 4 columns
-        // whose maximum reaches it is appended (its 4 raw scores + first code) with predicated stores.
+        // One 32-column chunk of this thread's row.  Fast path: maxima of the 8 groups of 4 columns (16
+        // ops) and their maximum (4 ops).  A chunk can only contribute candidates if its maximum reaches
+        // (running max - margin).  On short sweeps (K = 1024) some lane of the warp is in that case for
+        // ~85 % of the chunks (every lane sets ~ln(K/32) records plus its true winner), so the slow path
+        // is written for throughput: the slot of every qualifying group is a prefix sum of the predicates
+        // (no pointer chain, no write-after-read hazards on address registers between the stores).
         auto process = [&](uint32_t (&ra)[32], const int cbase) {
           float v[32];
 #pragma unroll
@@ -701,37 +722,35 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
               for (int i = 0; i < 32; ++i) out.dbg_scores[row * K_pad + col0 + cbase + i] = v[i];
             }
           }
-          float t[10];
+          float g[8];
 #pragma unroll
-          for (int i = 0; i < 10; ++i) t[i] = fmaxf(fmaxf(v[3 * i], v[3 * i + 1]), v[3 * i + 2]);
-          const float u0 = fmaxf(fmaxf(t[0], t[1]), t[2]), u1 = fmaxf(fmaxf(t[3], t[4]), t[5]);
-          const float u2 = fmaxf(fmaxf(t[6], t[7]), t[8]), u3 = fmaxf(fmaxf(t[9], v[30]), v[31]);
-          const float m = fmaxf(fmaxf(fmaxf(u0, u1), u2), u3);
+          for (int i = 0; i < 8; ++i) g[i] = fmaxf(fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), v[4 * i + 2]), v[4 * i + 3]);
+          const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), g[2]), fmaxf(fmaxf(fmaxf(g[3], g[4]), g[5]), fmaxf(g[6], g[7])));
           if (m >= runmax - margin) {
             // a maximum that beats the old one by more than the margin makes every listed entry stale
             if (m > runmax + margin) cnt = 0;
             runmax = fmaxf(runmax, m);
             const float thr = runmax - margin;
             if (cnt > LKEEP) cnt = list_compact(sc_base, co_base, cnt, thr, drop_addr);
-            uint32_t psc = sc_base + cnt * SC_STRIDE, pco = co_base + cnt * CO_STRIDE;
+            uint32_t slot[9];
+            slot[0] = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) slot[i + 1] = slot[i] + (g[i] >= thr ? 1u : 0u);
+            const uint32_t base_sc = sc_base + cnt * ENT_STRIDE, base_co = co_base + cnt * ENT_STRIDE;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float m4 = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
               asm volatile(
                   "{\n\t"
                   ".reg .pred p;\n\t"
-                  "setp.ge.f32 p, %2, %3;\n\t"
+                  "setp.ne.u32 p, %2, %3;\n\t"
                   "@p st.shared.v4.f32 [%0], {%4, %5, %6, %7};\n\t"
                   "@p st.shared.u32 [%1], %8;\n\t"
-                  "@p add.u32 %0, %0, %9;\n\t"
-                  "@p add.u32 %1, %1, %10;\n\t"
                   "}"
-                  : "+r"(psc), "+r"(pco)
-                  : "f"(m4), "f"(thr), "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]),
-                    "r"((uint32_t)(col0 + cbase + 4 * i)), "n"(SC_STRIDE), "n"(CO_STRIDE)
+                  ::"r"(base_sc + slot[i] * ENT_STRIDE), "r"(base_co + slot[i] * ENT_STRIDE), "r"(slot[i + 1]), "r"(slot[i]),
+                    "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]), "r"((uint32_t)(col0 + cbase + 4 * i))
                   : "memory");
             }
-            cnt = (pco - co_base) / CO_STRIDE;
+            cnt += slot[8];
           }
         };
 
