@@ -12,7 +12,7 @@ import subprocess
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libccvsq.so")
+LIB_PATH = os.environ.get("CCVSQ_LIB") or os.path.join(_HERE, "lib", "libccvsq.so")   # (override: A/B runs of two builds)
 CSRC_DIR = os.path.join(_HERE, "csrc")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ccvsq.h")
 
@@ -68,6 +68,7 @@ SIGNATURES = {
     "ccvsq_screen": (c_int, [_P, Layout, _P, _P, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P]),
     "ccvsq_screen_debug": (c_int, [_P, Layout, _P, _P, c_int, c_float, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                    _P, _P]),
+    "ccvsq_screen_trace": (c_int, [_P, Layout, _P, _P, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "ccvsq_rescore": (c_int, [_P, Layout, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "ccvsq_search_exact_rows": (c_int, [_P, Layout, _P, _P, c_int, _P, _P, c_int64, _P, _P]),
     "ccvsq_assign": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, _P, _P]),
@@ -108,6 +109,8 @@ def load() -> ctypes.CDLL:
         )
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in SIGNATURES.items():
+        if os.environ.get("CCVSQ_LIB") and not hasattr(lib, name):
+            continue             # an older build under A/B comparison may lack the newest diagnostics
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes

@@ -362,7 +362,9 @@ struct ScreenOut {
   uint8_t* dbg_flags;      // [N]
   float* dbg_margin;       // [N]
   float* dbg_scores;       // [N, K_pad]
+  long long* trace;        // [gridDim.x, TRACE_SWEEPS, 8] SM clock stamps of the pipeline hand-offs (DBG kernel only)
 };
+constexpr int TRACE_SWEEPS = 32;
 
 // Candidates of one row once all codes have been seen: every listed code with score >= runmax -
 // margin, sorted by (score desc, code asc), at most n_cand of them.  The list is in increasing code
@@ -561,8 +563,12 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
         const uint32_t a_tmem = tmem_base + TM_A + ab * a_cols;
         for (int j = 0; j < n_tiles; ++j) {
+          if (j == 0) { if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 0] = clock64(); } }
           mbar_wait(tmem_empty(b), b_phase ^ 1);
-          if (j == 0) mbar_wait(a_full(ab), a_phase);
+          if (j == 0) {
+            mbar_wait(a_full(ab), a_phase);
+            if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 1] = clock64(); }
+          }
           mbar_wait(full_bar(slot), phase);
           tc_fence_after();
           if (elect_one()) {
@@ -584,6 +590,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
             if (j == n_tiles - 1) umma_commit<CG>(a_empty(ab));   // last reader of this A buffer
           }
           __syncwarp();
+          if (j == n_tiles - 1) { if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 2] = clock64(); } }
           if (++slot == nslots) { slot = 0; phase ^= 1; }
           if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
         }
@@ -595,12 +602,17 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     // code sweeps (K = 1024) a 128 KiB row tile per CTA has to arrive within one sweep.  This warp runs
     // one row tile ahead of them and pulls the tile after next into L2 (fire-and-forget prefetches, no
     // registers or shared memory), so the loaders' global loads become L2 hits.
+    // (the first row tile is requested here as well: the loaders take it in four dependent rounds, and only
+    // their first round would otherwise be in flight while every CTA of the chip starts cold)
     uint32_t tl = 0;
-    for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
+    for (int gt = group - num_groups; gt < num_group_tiles; gt += num_groups) {
       const int gn = gt + num_groups;                     // the tile the loaders take after this one
       if (gn >= num_group_tiles) break;
-      const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
-      mbar_wait_sleep(a_empty(ab), a_phase ^ 1);          // the loaders are starting on tile gt now
+      if (gt >= group) {
+        const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
+        mbar_wait_sleep(a_empty(ab), a_phase ^ 1);        // the loaders are starting on tile gt now
+        ++tl;
+      }
       const int64_t n0 = ((int64_t)gn * CG + rank) * BM;
       if (n0 >= L.N) break;
       const int64_t n1 = (n0 + BM < L.N ? n0 + BM : L.N) - 1;
@@ -638,7 +650,9 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       }
       float va[32], vb[32];
       load_chunk(va, p, L.S, valid);            // in flight while waiting for the buffer
+      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 8 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 3] = clock64(); }
       mbar_wait_sleep(a_empty(ab), a_phase ^ 1);
+      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 8 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 4] = clock64(); }
       tc_fence_after();
       float ss = 0.f;
       const uint32_t dst = lane_base + ab * a_cols;
@@ -669,6 +683,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         }
       }
       tmem_st_wait();
+      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 8 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 5] = clock64(); }
       mbar_wait_sleep(norm_empty(ab), a_phase ^ 1);   // the epilogue has read the previous norms of this buffer
       norm_s[(ab * 2 + h) * BM + r] = ss;
       tc_fence_before();
@@ -693,6 +708,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
       const int64_t row = ((int64_t)gt * CG + rank) * BM + row_in_tile;
       mbar_wait(norm_full(ab), a_phase);
+      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 4 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 6] = clock64(); }
       const float margin = margin_scale * emax * sqrtf(norm_s[(ab * 2) * BM + row_in_tile] + norm_s[(ab * 2 + 1) * BM + row_in_tile]);
       __syncwarp();
       if (lane == 0) mbar_arrive(norm_empty(ab));
@@ -776,6 +792,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
       }
 
+      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 4 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 7] = clock64(); }
       if (row < L.N) finalize_row(sc_base, co_base, cnt, runmax, margin, drop_addr, n_cand, row, out);
     }
   }
@@ -838,7 +855,7 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
   CUtensorMap mb, mx;
   if (int rc = make_map(enc, &mb, E_bf16, K_pad, D + SCREEN_EXT, 64, BN / CG, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_map(enc, &mx, E_bf16, K_pad, D + SCREEN_EXT, 8, BN / CG, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-  auto kern = out.dbg_cand ? screen_kernel<CG, true, BN> : screen_kernel<CG, false, BN>;
+  auto kern = (out.dbg_cand || out.trace) ? screen_kernel<CG, true, BN> : screen_kernel<CG, false, BN>;
   if (int rc = enable_smem(kern, lay.total)) return rc;
   const int64_t rows_per_group = (int64_t)BM * CG;
   const int64_t group_tiles = (L.N + rows_per_group - 1) / rows_per_group;
@@ -936,6 +953,22 @@ extern "C" int ccvsq_screen(const float* z, ccvsq_layout lay, const void* E_bf16
   out.q_rows = queue_rows;
   out.q_cand = queue_cand;
   out.q_flags = queue_flags;
+  return screen_impl(z, lay, E_bf16, e_max, K, margin_tau, n_cand, out, 2, stream);
+}
+
+extern "C" int ccvsq_screen_trace(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
+                                  float margin_tau, int n_cand, int64_t* idx, int32_t* queue_count,
+                                  int32_t* queue_rows, int32_t* queue_cand, uint8_t* queue_flags, int64_t* trace,
+                                  void* stream) {
+  CCVSQ_REQUIRE(idx && queue_count && queue_rows && queue_cand && queue_flags && trace, CCVSQ_NULL_POINTER,
+                "screen_trace: null pointer");
+  ScreenOut out = {};
+  out.idx = idx;
+  out.q_count = queue_count;
+  out.q_rows = queue_rows;
+  out.q_cand = queue_cand;
+  out.q_flags = queue_flags;
+  out.trace = reinterpret_cast<long long*>(trace);
   return screen_impl(z, lay, E_bf16, e_max, K, margin_tau, n_cand, out, 2, stream);
 }
 

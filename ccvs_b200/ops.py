@@ -20,7 +20,7 @@ _L = _lib.load()  # fail loudly at import time if the extension is missing
 
 # kernels enqueued by each entry point (ccvsq_prepare_codebook: + one 4-byte memset node)
 _KERNELS_PER_CALL = {
-    "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
+    "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_trace": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
     "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1, "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1,
     "ccvsq_finalize": 1, "ccvsq_ema_update": 2,
     "ccvsq_quantize_forward": 0, "ccvsq_quantize_backward": 0,   # composites: counted by their wrappers
@@ -209,6 +209,18 @@ def screen(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, 
     _call("ccvsq_screen", _ptr(z), lay, _ptr(cb.e_bf16), _ptr(cb.e_max), cb.K, float(margin_tau), n_cand, _ptr(idx),
           _ptr(q.count), _ptr(q.rows), _ptr(q.cand), _ptr(q.flags), _stream(dev))
     return idx, q
+
+
+def screen_trace(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, margin_tau: float = 1.0):
+    """ccvsq_screen with the pipeline timeline (see ccvsq.h): returns (idx, queue, trace int64 [148, 32, 8])."""
+    dev = z.device
+    N = lay.rows
+    idx = torch.empty(N, dtype=torch.int64, device=dev)
+    q = _new_queue(N, n_cand, dev)
+    trace = torch.zeros(148, 32, 8, dtype=torch.int64, device=dev)
+    _call("ccvsq_screen_trace", _ptr(z), lay, _ptr(cb.e_bf16), _ptr(cb.e_max), cb.K, float(margin_tau), n_cand, _ptr(idx),
+          _ptr(q.count), _ptr(q.rows), _ptr(q.cand), _ptr(q.flags), _ptr(trace), _stream(dev))
+    return idx, q, trace
 
 
 @dataclass

@@ -115,6 +115,14 @@ int ccvsq_screen_debug(const float* z, ccvsq_layout lay, const void* E_bf16, con
                        int32_t* queue_rows, int32_t* queue_cand, uint8_t* queue_flags, int32_t* cand_idx,
                        float* cand_score, uint8_t* flags, float* row_margin, float* scores, void* stream);
 
+/* Timeline diagnostic (tools/trace_screen.py): ccvsq_screen plus SM-clock stamps of the pipeline hand-offs.
+ * trace [148, 32, 8] int64 (zeroed by the caller): per CTA and row tile (first 32): MMA warp {0: tile start,
+ * 1: A operand ready, 2: last MMA issued}, loader warp {3: ready to refill, 4: A buffer free, 5: A stored},
+ * epilogue warp {6: first accumulator wait, 7: sweep done}.                                        */
+int ccvsq_screen_trace(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
+                       float margin_tau, int n_cand, int64_t* idx, int32_t* queue_count, int32_t* queue_rows,
+                       int32_t* queue_cand, uint8_t* queue_flags, int64_t* trace, void* stream);
+
 /* ccvsq_rescore: re-evaluates the candidates of the queued rows in FP32 with the reference's
  * formula and lowest-index tie-break (quantize.py:45-50) and overwrites idx[row].  The queue length
  * is read on the device (no host sync).  Rows with queue_flags != 0 are passed on to the exact
