@@ -271,12 +271,17 @@ def main():
     prof_main = ops.PROFILER.summary()
     # keep the GPU under the same load until nvidia-smi has produced a few samples (its period is 100 ms,
     # a short timed region can end before the first one)
-    t_extra0 = time.perf_counter()
+    # (every rank runs the same number of extra steps: the training workload contains a collective)
     extra_steps = 0
+    if ms_total < 600.0:
+        extra_steps = min(5000, max(1, int(800.0 / max(ms_total / args.steps, 1e-3))))
+    if world > 1:
+        t = torch.tensor([extra_steps], device=dev, dtype=torch.int64)
+        dist.broadcast(t, src=0)
+        extra_steps = int(t)
     ops.PROFILER.reset(timing=False)
-    while rank == 0 and ms_total < 600.0 and time.perf_counter() - t_extra0 < 0.8:
+    for _ in range(extra_steps):
         step(z)
-        extra_steps += 1
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:

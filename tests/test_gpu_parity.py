@@ -249,7 +249,10 @@ def test_assign_gather_backward_stats_finalize():
 # 128-bit fast paths (stream_fast.cu): partial last tile, two channel slabs, mult > 1, row-major rows,
 # S not a multiple of the 32-position tile; each against plain torch math on the CPU
 FAST_CASES = [((3, 256, 6, 6), 300, 256, 1), ((2, 512, 8, 8), 128, 512, 1), ((5, 256, 4, 4), 64, 128, 2),
-              ((70, 256), 100, 256, 1), ((3, 64, 2, 10), 50, 64, 1), ((2, 3, 128, 8, 8), 1024, 128, 1)]
+              ((70, 256), 100, 256, 1), ((3, 64, 2, 10), 50, 64, 1), ((2, 3, 128, 8, 8), 1024, 128, 1),
+              # enough 32-position tiles per SM for the persistent cp.async pipeline (incl. two channel slabs, C < 256)
+              ((40, 256, 16, 16), 300, 256, 1), ((20, 512, 16, 16), 128, 512, 1), ((3, 80, 128, 8, 8), 64, 128, 1),
+              ((160, 64, 8, 8), 40, 64, 1)]
 
 
 @pytest.mark.parametrize("shape,K,D,mult", FAST_CASES)

@@ -45,3 +45,12 @@ timeit("backward dz only", lambda: ops.quantize_backward(z, lay, w, idx, g, one,
 timeit("backward dE only", lambda: ops.quantize_backward(z, lay, w, idx, None, one, 0.25, want_dz=False))
 timeit("code_stats", lambda: ops.code_stats(z, lay, w, K, idx, 1.0))
 timeit("empty ws", lambda: torch.empty(60 << 20, dtype=torch.uint8, device=dev))
+z2 = torch.empty_like(z)
+timeit("yardstick: torch copy (r+w)", lambda: z2.copy_(z))
+timeit("yardstick: torch fill (w)", lambda: z2.fill_(1.0))
+timeit("assign, no zq write", lambda: ops.assign(z, lay, w, idx, want_zq=False))
+idx0 = torch.zeros_like(idx)
+timeit("assign, all codes = 0 (E from L1)", lambda: ops.assign(z, lay, w, idx0))
+timeit("assign, codes = 0, no zq write", lambda: ops.assign(z, lay, w, idx0, want_zq=False))
+timeit("gather cm, all codes = 0", lambda: ops.gather(idx0, w, lay))
+timeit("gather rows, all codes = 0", lambda: ops.gather(idx0, w))
