@@ -394,3 +394,26 @@ def test_frozen_codebook_cache_and_polyak_update():
     inv = torch.empty(256, dtype=torch.int64)
     inv[perm] = torch.arange(256)
     assert torch.equal(i1.view(-1).cpu(), inv[i0.view(-1).cpu()])   # permuting rows permutes indices
+
+
+def test_host_pipeline_equals_whole_batch():
+    """ccvs_b200.pipeline: frame-chunked, copy/compute-overlapped quantization of a host batch returns what one
+    whole-batch forward returns (indices bit-exact; loss / perplexity to rounding)."""
+    from ccvs_b200.pipeline import HostQuantizePipeline
+    shape, K, D = (8, 4, 64, 8, 8), 256, 64
+    z, cb = vq_oracle.synth(shape, K, D, "T", seed=51)
+    vq = VectorQuantizer(K, D, 0.25).to(DEV).eval()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+        _, loss, (perp, _, idx) = vq(z.to(DEV))
+    pipe = HostQuantizePipeline(vq, shape, n_chunks=4, decode=True)
+    zh = z.pin_memory()
+    for _ in range(2):                      # second run exercises the slot-reuse events
+        idx_h, sc_h = pipe.run(zh)
+        pipe.synchronize()
+        torch.cuda.synchronize()
+    assert torch.equal(idx_h, idx.view(-1).cpu())
+    torch.testing.assert_close(sc_h[0], loss.cpu(), rtol=1e-5, atol=0)
+    torch.testing.assert_close(sc_h[1], perp.cpu(), rtol=1e-5, atol=0)
+    dec = torch.cat([d.reshape(-1, D) for d in pipe.decoded])
+    assert torch.equal(dec.cpu(), cb[idx.view(-1).cpu()])

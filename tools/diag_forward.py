@@ -54,3 +54,5 @@ timeit("assign, all codes = 0 (E from L1)", lambda: ops.assign(z, lay, w, idx0))
 timeit("assign, codes = 0, no zq write", lambda: ops.assign(z, lay, w, idx0, want_zq=False))
 timeit("gather cm, all codes = 0", lambda: ops.gather(idx0, w, lay))
 timeit("gather rows, all codes = 0", lambda: ops.gather(idx0, w))
+timeit("assign, no counts", lambda: ops.assign(z, lay, w, idx, want_counts=False))
+timeit("assign, no counts, no zq write", lambda: ops.assign(z, lay, w, idx, want_zq=False, want_counts=False))
