@@ -413,6 +413,38 @@ def main():
 
     cpu = None if args.no_cpu_baseline or world > 1 else cpu_baseline(args.workload)
 
+    # ---------------- small-batch latency (what the reference trainer actually issues) ----------------
+    small = None
+    if not train:
+        from ccvs_b200 import VectorQuantizer as _VQ
+        zs = z.view(clips * frames, D, h, w_)[:16].contiguous()      # 16 frames: BASELINE configs[0] geometry when h = w = 16
+        vqs = _VQ(K, D, 0.25).to(dev).eval()
+        with torch.no_grad():
+            vqs.embedding.weight.copy_(cb)
+
+        def eager():
+            with torch.no_grad():
+                _, _, (_, _, i) = vqs(zs)
+                vqs.embed_code(i.view(16, -1))
+
+        graphed = vqs.capture(zs, decode=True)
+
+        def time_calls(fn, n=200):
+            for _ in range(10):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        small = {"latents_per_call": int(zs.numel() // D), "layout": list(zs.shape), "K": K, "D": D,
+                 "ms_per_call_eager": time_calls(eager), "ms_per_call_cuda_graph": time_calls(graphed.replay),
+                 "note": "forward + embed_code; cuda_graph = VectorQuantizer.capture() replay (one driver call per step)"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -423,7 +455,7 @@ def main():
                    "l2": f"inputs larger than L2 ({z.numel() * 4 / 2**20:.0f} MiB of latents per step)",
                    "parallelism": f"frame-sharded x{world}, codebook replicated, no data-path collective"},
         "e2e": e2e, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        "kernel_breakdown": breakdown, "hbm_kernels": extra,
+        "kernel_breakdown": breakdown, "hbm_kernels": extra, "small_batch": small,
     }
     print(json.dumps(line))
     if world > 1:

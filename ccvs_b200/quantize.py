@@ -228,6 +228,10 @@ class VectorQuantizer(nn.Module):
         return ops.quantize_forward(z, lay, self.embedding.weight, self.beta, self.search_mode, self.n_cand,
                                     self.margin_tau, self.exact_fallback, cb=self._cb_cached(), indices_only=True).idx
 
+    def capture(self, z_static: torch.Tensor, decode: bool = False) -> "GraphedQuantizer":
+        """CUDA-graph the inference call for inputs of `z_static`'s shape (see GraphedQuantizer)."""
+        return GraphedQuantizer(self, z_static, decode=decode)
+
     def embed_code(self, code, channel_major_hw=None):
         """E[code] (quantize.py:76-83).  `channel_major_hw=(h, w)` additionally fuses the caller's
         NHWC->NCHW copy (quantized_video_model.py:833): code [G, h, w] -> [G, C, h, w]."""
@@ -259,6 +263,51 @@ class VectorQuantizer(nn.Module):
         err = getattr(self, "_last_gather_err", None)
         if err is not None and int(err.item()) != 0:
             raise IndexError("embed_code: index out of range in codebook")
+
+
+class GraphedQuantizer:
+    """One CUDA graph for a whole inference call of the quantizer on fixed-shape inputs.
+
+    The reference issues the quantizer on 1k-5k latents per call (scripts/*/train_frame_autoencoder.sh,
+    SURVEY A.5) and once per generated frame in the autoregressive re-encode loop
+    (quantized_video_model.py:870-904,939-947): at those sizes the six kernels of a forward take a few
+    microseconds each and the cost is launch latency.  `VectorQuantizer.capture(z_static)` records
+    forward (+ embed_code) once; `replay()` re-issues all kernels with a single driver call.  The caller
+    writes new latents into `z_static` (or passes them to `__call__`, which copies) and reads the static
+    outputs `z_q, loss, perplexity, indices[, decoded]`.  Inference only (no autograd through a graph).
+    """
+
+    def __init__(self, vq: "VectorQuantizer", z_static: torch.Tensor, decode: bool = False, warmup: int = 2):
+        if not z_static.is_cuda:
+            raise RuntimeError("CUDA only; there is no CPU fallback")
+        self.vq = vq
+        self.z = z_static
+        self.decode = decode
+        lead = z_static.shape[0] if z_static.ndim < 5 else z_static.shape[0] * z_static.shape[1]
+
+        def run():
+            z_q, loss, (perp, _, idx) = vq(self.z)
+            dec = vq.embed_code(idx.view(lead, -1)) if decode else None
+            return z_q, loss, perp, idx, dec
+
+        side = torch.cuda.Stream(z_static.device)
+        side.wait_stream(torch.cuda.current_stream(z_static.device))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(warmup):              # module loading, shared-memory opt-ins, allocator warm-up
+                run()
+        torch.cuda.current_stream(z_static.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.z_q, self.loss, self.perplexity, self.indices, self.decoded = run()
+
+    def replay(self):
+        self.graph.replay()
+        return self.z_q, self.loss, (self.perplexity, None, self.indices)
+
+    def __call__(self, z: Optional[torch.Tensor] = None):
+        if z is not None and z.data_ptr() != self.z.data_ptr():
+            self.z.copy_(z)
+        return self.replay()
 
 
 class EMAVectorQuantizer(VectorQuantizer):

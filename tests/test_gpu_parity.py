@@ -417,3 +417,30 @@ def test_host_pipeline_equals_whole_batch():
     torch.testing.assert_close(sc_h[1], perp.cpu(), rtol=1e-5, atol=0)
     dec = torch.cat([d.reshape(-1, D) for d in pipe.decoded])
     assert torch.equal(dec.cpu(), cb[idx.view(-1).cpu()])
+
+
+def test_cuda_graph_replay_matches_eager():
+    """VectorQuantizer.capture: one graph launch per call (small-batch / per-frame re-encode regime)."""
+    shape, K, D = (16, 256, 16, 16), 1024, 256            # BASELINE config 1
+    z, cb = vq_oracle.synth(shape, K, D, "T", seed=61)
+    z2, _ = vq_oracle.synth(shape, K, D, "T", seed=62)
+    vq = VectorQuantizer(K, D, 0.25).to(DEV).eval()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+    zs = z.to(DEV).clone()
+    g = vq.capture(zs, decode=True)
+    for zin in (z, z2, z):
+        zq_g, loss_g, (perp_g, _, idx_g) = g(zin.to(DEV))
+        with torch.no_grad():
+            zq, loss, (perp, _, idx) = vq(zin.to(DEV))
+            dec = vq.embed_code(idx.view(shape[0], -1))
+        assert torch.equal(idx_g, idx) and torch.equal(zq_g, zq) and torch.equal(g.decoded, dec)
+        torch.testing.assert_close(loss_g, loss, rtol=1e-6, atol=0)
+        torch.testing.assert_close(perp_g, perp, rtol=1e-6, atol=0)
+    # the codebook is re-read on every replay (Polyak averaging writes it in place)
+    with torch.no_grad():
+        vq.embedding.weight.data.copy_(cb.flip(0).to(DEV))
+    _, _, (_, _, idx_f) = g(z.to(DEV))
+    res = vq_oracle.forward(z, cb.flip(0), 0.25)
+    par = vq_oracle.classify_indices(idx_f.view(-1).cpu(), vq_oracle.to_channel_last(z).reshape(-1, D), cb.flip(0))
+    assert par.mismatch == 0 and par.agreement >= 0.9999, par
