@@ -77,6 +77,8 @@ SIGNATURES = {
     "ccvsq_code_stats": (c_int, [_P, Layout, _P, c_int, _P, c_float, _P, _P, _P]),
     "ccvsq_finalize": (c_int, [_P, _P, _P, _P, c_int, c_int, c_double, c_double, c_float, _P, _P, _P, _P]),
     "ccvsq_ema_update": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
+    "ccvsq_gather_add": (c_int, [_P, _P, c_int, c_int, c_int64, _P, c_int64, _P, _P, _P]),
+    "ccvsq_polyak": (c_int, [_P, _P, c_int64, c_double, _P]),
     "ccvsq_forward_workspace_bytes": (c_uint64, [c_int64, c_int, c_int, c_int, c_int, c_int]),
     "ccvsq_quantize_forward": (c_int, [POINTER(ForwardArgs), _P]),
     "ccvsq_quantize_backward": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, c_float, _P, _P, _P, _P]),

@@ -125,6 +125,8 @@ struct StreamArgs {
   float coef_scale;       // backward: 2 / M
   float sub;              // stats: resid += x - sub * E[idx]
   int32_t* err_flag;      // gather
+  const float* pos;       // gather (row-major only): rows added to the gathered rows, out[n] = E[idx[n]] + pos[n % pos_period]
+  int64_t pos_period;
   int K;
   FinArgs fin;
 };

@@ -306,6 +306,10 @@ __global__ void __launch_bounds__(FNT) rows4_kernel(const StreamArgs a, const in
         out[j] = e[j];
       }
     }
+    if (MODE == MODE_GATHER && a.pos) {
+      const float4 pv = __ldg(reinterpret_cast<const float4*>(a.pos) + (row[u] % a.pos_period) * Q + q[u]);
+      out[0] = __fadd_rn(out[0], pv.x); out[1] = __fadd_rn(out[1], pv.y); out[2] = __fadd_rn(out[2], pv.z); out[3] = __fadd_rn(out[3], pv.w);
+    }
     if (MODE != MODE_STATS && a.out) {
       float4* dst = reinterpret_cast<float4*>(a.out) + cb + o;
       const float4 v = *reinterpret_cast<const float4*>(out);
@@ -394,6 +398,10 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kern
           out[t] = e[t];
         }
       }
+      if (MODE == MODE_GATHER && a.pos) {
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(a.pos) + ((n_base + i) % a.pos_period) * Q + j);
+        out[0] = __fadd_rn(out[0], pv.x); out[1] = __fadd_rn(out[1], pv.y); out[2] = __fadd_rn(out[2], pv.z); out[3] = __fadd_rn(out[3], pv.w);
+      }
       if (MODE != MODE_STATS && a.out) {
         float4* dst = reinterpret_cast<float4*>(a.out) + (n_base + i) * Q + j;
         const float4 v = *reinterpret_cast<const float4*>(out);
@@ -428,7 +436,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kern
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 bool stream_fast_supported(const StreamArgs& a, const Lay& L) {
-  if (!aligned16(a.x) || !aligned16(a.g) || !aligned16(a.E) || !aligned16(a.out) || !aligned16(a.resid)) return false;
+  if (!aligned16(a.x) || !aligned16(a.g) || !aligned16(a.E) || !aligned16(a.out) || !aligned16(a.resid) || !aligned16(a.pos)) return false;
   if (L.D % 4 != 0) return false;
   if (L.S == 1) return true;
   if (L.S % 4 != 0 || L.C % 32 != 0) return false;

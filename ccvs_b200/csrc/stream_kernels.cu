@@ -447,6 +447,14 @@ __global__ void ema_embed_kernel(float* __restrict__ E, const float* __restrict_
   }
 }
 
+// Polyak average of the codebook (quantized_video_model.py:951-964):
+//   par_ema.data.mul_(decay).add_(par.data, alpha=1-decay)
+__global__ void polyak_kernel(float* __restrict__ ema, const float* __restrict__ live, size_t n, float decay,
+                              float alpha) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    ema[i] = fmaf(alpha, live[i], __fmul_rn(ema[i], decay));
+}
+
 }  // namespace ccvsq
 
 // =================================================================================================
@@ -595,6 +603,31 @@ extern "C" int ccvsq_gather(const int64_t* code, const float* E, int K, ccvsq_la
   StreamArgs a = {};
   a.E = E; a.idx = code; a.out = out; a.err_flag = err_flag; a.K = K;
   return stream_launch(MODE_GATHER, a, L, (cudaStream_t)stream);
+}
+
+extern "C" int ccvsq_gather_add(const int64_t* code, const float* table, int K, int D, int64_t N, const float* pos,
+                                int64_t pos_period, float* out, int32_t* err_flag, void* stream) {
+  CCVSQ_REQUIRE(code && table && pos && out, CCVSQ_NULL_POINTER, "gather_add: null pointer");
+  CCVSQ_REQUIRE(K > 0 && D > 0 && N > 0 && pos_period > 0, CCVSQ_BAD_SHAPE, "gather_add: K=%d D=%d N=%lld period=%lld", K,
+                D, (long long)N, (long long)pos_period);
+  Lay L;
+  ccvsq_layout lay = {N, D, 1, 1};
+  if (int rc = make_lay(lay, &L)) return rc;
+  StreamArgs a = {};
+  a.E = table; a.idx = code; a.out = out; a.err_flag = err_flag; a.K = K; a.pos = pos; a.pos_period = pos_period;
+  CCVSQ_REQUIRE(stream_fast_supported(a, L), CCVSQ_UNSUPPORTED,
+                "gather_add: needs D %% 4 == 0 and 16-byte aligned table / pos / out (D=%d)", D);
+  return stream_fast_launch(MODE_GATHER, a, L, (cudaStream_t)stream);
+}
+
+extern "C" int ccvsq_polyak(float* ema, const float* live, int64_t n, double decay, void* stream) {
+  CCVSQ_REQUIRE(ema && live, CCVSQ_NULL_POINTER, "polyak: null pointer");
+  CCVSQ_REQUIRE(n > 0, CCVSQ_BAD_SHAPE, "polyak: n=%lld", (long long)n);
+  int blocks = cdiv(n, 256 * 4);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  polyak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ema, live, (size_t)n, (float)decay, (float)(1.0 - decay));
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
 }
 
 extern "C" int ccvsq_finalize(const float* resid, const int32_t* counts, const double* sq_err,

@@ -23,6 +23,7 @@ _KERNELS_PER_CALL = {
     "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_trace": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
     "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1, "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1,
     "ccvsq_finalize": 1, "ccvsq_ema_update": 2,
+    "ccvsq_gather_add": 1, "ccvsq_polyak": 1,
     "ccvsq_quantize_forward": 0, "ccvsq_quantize_backward": 0,   # composites: counted by their wrappers
 }
 
@@ -328,6 +329,32 @@ def gather(code: torch.Tensor, weight: torch.Tensor, out_lay: Optional[Layout] =
         return out, err
     _call("ccvsq_gather", _ptr(code), _ptr(w), K, out_lay, _ptr(out), _ptr(err), _stream(dev))
     return out, err
+
+
+def gather_add(code: torch.Tensor, table: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """tok_emb(idx) + pos_emb of the prior (mingpt.py:234-236) in one pass: code [B, T] int64, table [K, D],
+    pos [1, >=T, D] or [>=T, D] -> [B, T, D] with out[b, t] = table[code[b, t]] + pos[t]."""
+    _req(code, torch.int64, "code")
+    w = _req(table.detach(), torch.float32, "table")
+    K, D = w.shape
+    B, T = code.shape
+    p2 = pos.detach().reshape(-1, D)[:T]
+    p2 = _req(p2.contiguous(), torch.float32, "pos")
+    if p2.shape[0] < T:
+        raise ValueError(f"position table has {p2.shape[0]} rows, need {T}")
+    out = torch.empty(B, T, D, dtype=torch.float32, device=w.device)
+    err = torch.zeros(1, dtype=torch.int32, device=w.device)
+    _call("ccvsq_gather_add", _ptr(code), _ptr(w), K, D, B * T, _ptr(p2), T, _ptr(out), _ptr(err), _stream(w.device))
+    return out, err
+
+
+def polyak(ema: torch.Tensor, live: torch.Tensor, decay: float) -> None:
+    """ema <- decay*ema + (1-decay)*live in place (quantized_video_model.py:951-964), one launch."""
+    _req(ema, torch.float32, "ema")
+    _req(live, torch.float32, "live")
+    if ema.shape != live.shape:
+        raise ValueError("shape mismatch")
+    _call("ccvsq_polyak", _ptr(ema), _ptr(live), ema.numel(), float(decay), _stream(ema.device))
 
 
 def backward_dz(z, lay: Layout, weight, idx, g_zq: Optional[torch.Tensor], g_loss: torch.Tensor) -> torch.Tensor:

@@ -228,6 +228,21 @@ class VectorQuantizer(nn.Module):
         return ops.quantize_forward(z, lay, self.embedding.weight, self.beta, self.search_mode, self.n_cand,
                                     self.margin_tau, self.exact_fallback, cb=self._cb_cached(), indices_only=True).idx
 
+    @torch.no_grad()
+    def accumulate_from(self, live: "VectorQuantizer", decay: float = 0.999):
+        """Polyak step of the reference's `accumulate()` for the quantizer (quantized_video_model.py:951-964,
+        `acc(self.net_q_ema, self.net_q, decay)`): self.embedding.weight <- decay*self + (1-decay)*live, written
+        through `.data` in place exactly like the reference (no autograd version bump)."""
+        ops.polyak(self.embedding.weight.data, live.embedding.weight.data, decay)
+        return self
+
+    def embed_tokens(self, code: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor):
+        """Indices -> prior hand-off (mingpt.py:234-236): tok_emb(code) + pos_emb in one gather pass.
+        code [B, T] int64 (what QVidModel.encode returns, quantized_video_model.py:799)."""
+        out, err = ops.gather_add(code.contiguous(), tok_emb, pos_emb)
+        self._last_gather_err = err
+        return out
+
     def capture(self, z_static: torch.Tensor, decode: bool = False) -> "GraphedQuantizer":
         """CUDA-graph the inference call for inputs of `z_static`'s shape (see GraphedQuantizer)."""
         return GraphedQuantizer(self, z_static, decode=decode)

@@ -163,6 +163,21 @@ int ccvsq_assign(const float* z, ccvsq_layout lay, const float* E, int K, const 
 int ccvsq_gather(const int64_t* code, const float* E, int K, ccvsq_layout out_lay, float* out,
                  int32_t* err_flag, void* stream);
 
+/* ---- indices -> prior hand-off -------------------------------------------------
+ * The transformer prior starts with  tok_emb(idx) + pos_emb  (mingpt.py:234-236: an nn.Embedding gather
+ * of [K, n_embd] rows followed by a broadcast add of the [1, T, n_embd] position table).  Same gather
+ * kernel, different table, the add fused into the store:
+ *   out[n, :] = fl(table[code[n], :] + pos[n % pos_period, :])      n = b*T + t, pos_period = T
+ * Requires D % 4 == 0 and 16-byte aligned pointers; codes outside [0,K) set *err_flag (may be NULL). */
+int ccvsq_gather_add(const int64_t* code, const float* table, int K, int D, int64_t N, const float* pos,
+                     int64_t pos_period, float* out, int32_t* err_flag, void* stream);
+
+/* ---- Polyak average of the codebook (quantized_video_model.py:951-964, --q_use_ema) ------------
+ *   ema[i] = fl(fl(ema[i]*float(decay)) + float(1-decay)*live[i])   in place, one launch (decay is a double like the
+ *   Python scalar of the reference, so 1-decay is formed before the cast)
+ * (the reference issues par_ema.data.mul_(decay).add_(par.data, alpha=1-decay): two launches per parameter) */
+int ccvsq_polyak(float* ema, const float* live, int64_t n, double decay, void* stream);
+
 /* ---- backward: straight-through + commitment gradient ---------------------------------------
  * Replaces the autograd graph of quantize.py:60-64:
  *   dz = g_zq + (2*g_loss/M) * (z - E[idx]),   M = numel(z)

@@ -444,3 +444,38 @@ def test_cuda_graph_replay_matches_eager():
     res = vq_oracle.forward(z, cb.flip(0), 0.25)
     par = vq_oracle.classify_indices(idx_f.view(-1).cpu(), vq_oracle.to_channel_last(z).reshape(-1, D), cb.flip(0))
     assert par.mismatch == 0 and par.agreement >= 0.9999, par
+
+
+def test_polyak_and_prior_handoff():
+    """SURVEY 8a row a15 (Polyak average of the codebook) and 8f N2 (tok_emb gather + positional add)."""
+    torch.manual_seed(71)
+    K, D = 1024, 256
+    a, b = VectorQuantizer(K, D, 0.25).to(DEV), VectorQuantizer(K, D, 0.25).to(DEV)
+    with torch.no_grad():
+        a.embedding.weight.copy_(torch.randn(K, D))
+        b.embedding.weight.copy_(torch.randn(K, D))
+    ref = a.embedding.weight.detach().cpu().clone()
+    for _ in range(3):
+        ref = vq_oracle.polyak(ref, b.embedding.weight.detach().cpu(), 0.999)
+        v0 = a.embedding.weight._version
+        a.accumulate_from(b, 0.999)
+        assert a.embedding.weight._version == v0              # .data write, like the reference
+    torch.testing.assert_close(a.embedding.weight.detach().cpu(), ref, rtol=1e-6, atol=1e-7)
+
+    n_embd, T, B = 1024, 320, 6                                # mingpt: n_embd 1024, a 5-frame 8x8 window
+    tok = torch.randn(K, n_embd)
+    pos = torch.randn(1, 1280, n_embd) * 0.02
+    code = torch.randint(0, K, (B, T))
+    out = a.embed_tokens(code.to(DEV), tok.to(DEV), pos.to(DEV))
+    a.check_codes()
+    assert torch.equal(out.cpu(), vq_oracle.embed_tokens(code, tok, pos))       # one rounding: bit-exact
+    bad = code.clone()
+    bad[2, 5] = K + 3
+    a.embed_tokens(bad.to(DEV), tok.to(DEV), pos.to(DEV))
+    with pytest.raises(IndexError):
+        a.check_codes()
+    # a table whose width is not a multiple of 128 takes the flat 16-byte kernel
+    tok2, pos2 = torch.randn(50, 72), torch.randn(1, 40, 72)
+    code2 = torch.randint(0, 50, (3, 40))
+    out2, _ = ops.gather_add(code2.to(DEV), tok2.to(DEV), pos2.to(DEV))
+    assert torch.equal(out2.cpu(), vq_oracle.embed_tokens(code2, tok2, pos2))

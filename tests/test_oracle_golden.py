@@ -108,3 +108,15 @@ def test_ema_restatement_fixed_point():
     new_cb, n, s = vq_oracle.ema_update(cb, torch.full((8,), 8.0), cb * 8.0, rows, idx, decay=0.9, eps=0.0)
     torch.testing.assert_close(new_cb, cb, rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(n, torch.full((8,), 8.0))
+
+
+def test_oracle_polyak_and_embed_tokens_shapes():
+    """The checker's restatements of the caller-side rows (quantized_video_model.py:951-964, mingpt.py:234-236)."""
+    import torch
+    import vq_oracle
+    ema, live = torch.ones(4, 3), torch.zeros(4, 3)
+    out = vq_oracle.polyak(ema, live, 0.999)
+    assert torch.allclose(out, torch.full((4, 3), 0.999)) and torch.equal(ema, torch.ones(4, 3))
+    tok, pos = torch.arange(12.).view(4, 3), torch.ones(1, 5, 3)
+    e = vq_oracle.embed_tokens(torch.tensor([[0, 3], [1, 1]]), tok, pos)
+    assert e.shape == (2, 2, 3) and torch.equal(e[0, 1], tok[3] + 1)
