@@ -26,6 +26,22 @@ constexpr int FPT = 32;    // positions per tile
 constexpr int FNT = 256;   // threads per CTA
 constexpr int FSLAB = 256; // channels per CTA (a tile is FPT x slab)
 
+// 16-byte global -> shared copy that bypasses the register file (LDGSTS, L2-only caching: codebook rows are
+// scattered, a line is rarely reused by the same SM)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+#ifndef CCVSQ_PREFETCH_WAVES
+#define CCVSQ_PREFETCH_WAVES 1
+#endif
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -70,7 +86,14 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : 4) cm4_kernel
   __shared__ float s_red[FNT / 32];
   __shared__ bool s_last;
   const int tid = threadIdx.x;
-  const int64_t p0 = (int64_t)blockIdx.x * FPT;
+  // assign walks the tiles from the end: it runs right after the search, which read the latents front to back, so
+  // the tail of z is what the L2 still holds (126 MB) — those tiles are re-read on chip instead of from HBM
+  #ifdef CCVSQ_ASSIGN_FORWARD_ORDER
+  const uint32_t bx = blockIdx.x;
+#else
+  const uint32_t bx = MODE == MODE_ASSIGN ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+#endif
+  const int64_t p0 = (int64_t)bx * FPT;
   const int np = (int)min((int64_t)FPT, L.P - p0);
   const int c_lo = (int)blockIdx.y * CS;
   const int QS = CS >> 2;                           // 16-byte chunks per tile row
@@ -88,9 +111,27 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : 4) cm4_kernel
   int64_t tile_base = 0;
   if (tile_in_group) {
     const uint32_t tpg = (uint32_t)L.S >> 5;        // tiles per group
-    const uint32_t g = blockIdx.x / tpg;
-    const uint32_t s0 = (blockIdx.x - g * tpg) << 5;
+    const uint32_t g = bx / tpg;
+    const uint32_t s0 = (bx - g * tpg) << 5;
     tile_base = ((int64_t)g * L.C + c_lo) * L.S + s0;
+  }
+  // ---- L2 prefetch of the tile one wave of CTAs ahead (fire and forget, no registers): the demand loads of
+  // that tile then hit in L2, and HBM sees twice the requests in flight (these kernels are latency-bound: every
+  // CTA goes idx -> codebook rows -> compute -> store, and only 4 CTAs fit an SM)
+  if (tile_in_group) {
+    const int64_t ahead = (int64_t)CCVSQ_PREFETCH_WAVES * kNumSMs * (MODE == MODE_BACKWARD ? 2 : 4);
+    const int64_t nb = MODE == MODE_ASSIGN ? (int64_t)bx - ahead : (int64_t)bx + ahead;
+    if (nb >= 0 && nb < (int64_t)gridDim.x) {
+      const uint32_t tpg = (uint32_t)L.S >> 5;
+      const uint32_t g = (uint32_t)nb / tpg;
+      const uint32_t s0 = ((uint32_t)nb - g * tpg) << 5;
+      const int64_t nbase = ((int64_t)g * L.C + c_lo) * L.S + s0;
+      for (int c = tid; c < CS; c += FNT) {
+        if (HAS_X) prefetch_l2(a.x + nbase + (int64_t)c * L.S);
+        if (has_g) prefetch_l2(a.g + nbase + (int64_t)c * L.S);
+      }
+      if (tid < (FPT * L.mult + 15) / 16) prefetch_l2(a.idx + nb * FPT * L.mult + tid * 16);
+    }
   }
 #pragma unroll
   for (int it = 0; it < MAXIT; ++it) {
@@ -120,21 +161,37 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : 4) cm4_kernel
     }
   }
 
-  // ---- gather the codebook rows of this tile into shared memory: one warp per position, lanes over
-  // the 16-byte chunks of the row (QS <= 64: at most two per lane)
+  // ---- gather the codebook rows of this tile into shared memory: one warp per position (4 positions per warp),
+  // lanes over the 16-byte chunks of the row (QS <= 64: at most two per lane).  The four codes of a warp are read
+  // by four lanes in ONE load and broadcast, and the rows go global -> shared with cp.async: the whole 32 KiB gather
+  // of the tile is in flight at once next to the latent loads above, without a register round trip.
   if (need_e) {
     const int warp = tid >> 5, lane = tid & 31;
-    for (int p = warp; p < np; p += FNT / 32) {
-      const int sw = (p >> 2) & 7;
-      if (L.mult == 1) {
-        int64_t k = __ldg(a.idx + p0 + p);
-        if (k < 0 || k >= a.K) {
-          if (MODE == MODE_GATHER) { if (a.err_flag && lane == 0) atomicOr(a.err_flag, 1); k = 0; }
-          else k = k < 0 ? 0 : a.K - 1;
+    if (L.mult == 1) {
+      int64_t kk = 0;
+      {
+        const int p = warp + (FNT / 32) * lane;
+        if (lane < FPT / (FNT / 32) && p < np) {
+          kk = __ldg(a.idx + p0 + p);
+          if (kk < 0 || kk >= a.K) {
+            if (MODE == MODE_GATHER) { if (a.err_flag) atomicOr(a.err_flag, 1); kk = 0; }
+            else kk = kk < 0 ? 0 : a.K - 1;
+          }
         }
-        const float4* src = reinterpret_cast<const float4*>(a.E + (size_t)k * L.D + c_lo);
-        for (int q = lane; q < QS; q += 32) tile4[p * QS + (q ^ sw)] = __ldg(src + q);
-      } else {
+      }
+#pragma unroll
+      for (int i = 0; i < FPT / (FNT / 32); ++i) {
+        const int p = warp + (FNT / 32) * i;
+        const int64_t k = __shfl_sync(0xffffffffu, kk, i);
+        if (p < np) {
+          const int sw = (p >> 2) & 7;
+          const float4* src = reinterpret_cast<const float4*>(a.E + (size_t)k * L.D + c_lo);
+          for (int q = lane; q < QS; q += 32) cp_async16(&tile4[p * QS + (q ^ sw)], src + q);
+        }
+      }
+    } else {
+      for (int p = warp; p < np; p += FNT / 32) {
+        const int sw = (p >> 2) & 7;
         for (int q = lane; q < QS; q += 32) {
           const int c = c_lo + 4 * q;
           const int m = c / L.D, j = c - m * L.D;
@@ -143,7 +200,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : 4) cm4_kernel
             if (MODE == MODE_GATHER) { if (a.err_flag) atomicOr(a.err_flag, 1); k = 0; }
             else k = k < 0 ? 0 : a.K - 1;
           }
-          tile4[p * QS + (q ^ sw)] = __ldg(reinterpret_cast<const float4*>(a.E + (size_t)k * L.D + j));
+          cp_async16(&tile4[p * QS + (q ^ sw)], a.E + (size_t)k * L.D + j);
         }
       }
     }
@@ -156,6 +213,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : 4) cm4_kernel
       if (k >= 0 && k < a.K) atomicAdd(a.counts + k, 1);
     }
   }
+  cp_async_wait_all();
   __syncthreads();
 
   float coef = 0.f;
@@ -352,6 +410,10 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kern
   const bool need_e = MODE != MODE_STATS || a.sub != 0.f;
   int64_t k[RPW];
   bool valid[RPW];
+  {  // codes of the CTA one wave ahead -> L2 (a CTA covers 32 rows = two 128-byte lines of idx)
+    const int64_t nb = ((int64_t)blockIdx.x + (int64_t)CCVSQ_PREFETCH_WAVES * kNumSMs * 8) * (FNT / 32) * RPW;
+    if (threadIdx.x < 2 && nb + 16 * threadIdx.x < N) prefetch_l2(a.idx + nb + 16 * threadIdx.x);
+  }
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
     const int64_t n = n_base + i;
