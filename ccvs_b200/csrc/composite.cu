@@ -21,7 +21,7 @@ WsPlan plan_workspace(int64_t N, int K, int D, int n_cand, bool with_codebook, b
     p.e_bf16 = off; off += tensor ? align_up((size_t)ccvsq_codebook_rows(K) * (D + SCREEN_EXT) * 2) : 0;
   }
   if (tensor) {
-    p.fb_cap = N < 65536 ? N : 65536;
+    p.fb_cap = N;   // every row may be flagged (e.g. a collapsed codebook: all codes tie inside the margin)
     p.q_rows = off;  off += align_up((size_t)N * 4);
     p.q_cand = off;  off += align_up((size_t)N * n_cand * 4);
     p.q_flags = off; off += align_up((size_t)N);

@@ -254,7 +254,7 @@ def screen_debug(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int
 
 
 def rescore(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, idx: torch.Tensor, q: ScreenQueue,
-            exact_fallback: bool = True, fallback_capacity: int = 1 << 16) -> torch.Tensor:
+            exact_fallback: bool = True, fallback_capacity: Optional[int] = None) -> torch.Tensor:
     """FP32 re-scoring of the queued rows (in place on idx); flagged rows go to the exact kernel."""
     dev = z.device
     N = lay.rows
@@ -262,7 +262,7 @@ def rescore(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, idx: torch.Tenso
     fb_rows = fb_count = None
     cap = 0
     if exact_fallback:
-        cap = min(N, fallback_capacity)
+        cap = N if fallback_capacity is None else min(N, fallback_capacity)   # default: room for every row
         fb_rows = torch.empty(2 * cap, dtype=torch.int64, device=dev)     # rows | packed keys
         fb_count = torch.zeros(2, dtype=torch.int32, device=dev)          # queued rows, scratch counter
     _call("ccvsq_rescore", _ptr(z), lay, _ptr(cb.weight), _ptr(cb.e_sq), cb.K, n_cand, _ptr(q.count), _ptr(q.rows),
@@ -309,9 +309,11 @@ def assign(z: torch.Tensor, lay: Layout, weight: torch.Tensor, idx: torch.Tensor
     return zq, sq, counts
 
 
-def gather(code: torch.Tensor, weight: torch.Tensor, out_lay: Optional[Layout] = None) -> torch.Tensor:
+def gather(code: torch.Tensor, weight: torch.Tensor, out_lay: Optional[Layout] = None,
+           err: Optional[torch.Tensor] = None) -> torch.Tensor:
     """embed_code (quantize.py:76-83): E[code].  With a channel-major `out_lay` (S>1) the result is
-    written directly as [G, C, S] (the decoder's layout)."""
+    written directly as [G, C, S] (the decoder's layout).  `err` (int32 [1], zeroed by the caller) receives a
+    sticky 1 if a code lies outside [0, K); a fresh flag is allocated when it is not given."""
     _req(code, torch.int64, "code")
     w = _req(weight.detach(), torch.float32, "codebook")
     K, D = w.shape
@@ -324,7 +326,8 @@ def gather(code: torch.Tensor, weight: torch.Tensor, out_lay: Optional[Layout] =
         if out_lay.rows != n or out_lay.dim != D:
             raise ValueError("out_lay does not match code/codebook shape")
         out = torch.empty(out_lay.G, out_lay.C, out_lay.S, dtype=torch.float32, device=dev)
-    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    if err is None:
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
     if n == 0:
         return out, err
     _call("ccvsq_gather", _ptr(code), _ptr(w), K, out_lay, _ptr(out), _ptr(err), _stream(dev))

@@ -256,15 +256,16 @@ class VectorQuantizer(nn.Module):
         code = code.contiguous()
         if code.dtype != torch.int64:
             code = code.to(torch.int64)
+        flag = self._gather_flag(w.device)
         if channel_major_hw is not None:
             h, wd = channel_major_hw
             S = h * wd
             n_pos = code.numel() // self.mult
             lay = Layout(n_pos // S, self.e_dim * self.mult, S, self.mult)
-            out, err = ops.gather(code, w, lay)
+            out, err = ops.gather(code, w, lay, err=flag)
             z = out.view(-1, self.e_dim * self.mult, h, wd)
         else:
-            z, err = ops.gather(code, w)
+            z, err = ops.gather(code, w, err=flag)
             if self.mult > 1:
                 s = list(z.shape)
                 s[-1] *= self.mult
@@ -273,10 +274,21 @@ class VectorQuantizer(nn.Module):
         self._last_gather_err = err   # device flag: nonzero if a code was outside [0, n_e)
         return z
 
+    def _gather_flag(self, dev) -> torch.Tensor:
+        """Persistent device flag of embed_code (one int32, zeroed once): the gather kernels OR a 1 into it when a
+        code is out of range, so a call costs no extra fill launch; `check_codes()` reads and clears it."""
+        f = getattr(self, "_gather_err_buf", None)
+        if f is None or f.device != dev:
+            f = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._gather_err_buf = f
+        return f
+
     def check_codes(self):
-        """Synchronising check of the last embed_code (nn.Embedding raises on out-of-range codes)."""
+        """Synchronising check of the embed_code calls since the last check (nn.Embedding raises on out-of-range
+        codes); clears the flag."""
         err = getattr(self, "_last_gather_err", None)
         if err is not None and int(err.item()) != 0:
+            err.zero_()
             raise IndexError("embed_code: index out of range in codebook")
 
 

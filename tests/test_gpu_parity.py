@@ -479,3 +479,27 @@ def test_polyak_and_prior_handoff():
     code2 = torch.randint(0, 50, (3, 40))
     out2, _ = ops.gather_add(code2.to(DEV), tok2.to(DEV), pos2.to(DEV))
     assert torch.equal(out2.cpu(), vq_oracle.embed_tokens(code2, tok2, pos2))
+
+
+def test_collapsed_codebook_every_row_falls_back():
+    """A collapsed codebook (all codes within 1e-6 of one vector: what k-means-free VQ training produces right
+    after a bad init) puts every code of every row inside the screening margin, so ALL rows go to the exact FP32
+    fallback — more than the 65 536 rows the fallback list used to hold.  The result must still be the FP32 argmin."""
+    torch.manual_seed(5)
+    K, D, N = 256, 64, 1 << 17
+    base = torch.randn(1, D)
+    cb = (base + 1e-6 * torch.randn(K, D)).contiguous()
+    z = (base + 0.5 * torch.randn(N, D)).contiguous()
+    lay = ops.layout_of(z.shape, D, 1)
+    pcb = ops.prepare_codebook(cb.to(DEV))
+    zt = z.to(DEV)
+    idx_t = ops.search(zt, lay, pcb, mode="tensor")
+    idx_e = ops.search(zt, lay, pcb, mode="exact")
+    assert torch.equal(idx_t, idx_e)
+    out = ops.quantize_forward(zt, lay, cb.to(DEV), 0.25, mode="tensor")
+    assert torch.equal(out.idx.view(-1), idx_e)
+    # against the CPU oracle only the tie band can be checked here: all K distances of a row lie within ~1e-6
+    # relative of each other, and d = (||z||^2 + ||e||^2) - 2 z.e cancels from ~150 down to ~16, so one ulp of the
+    # sums is already 1e-6 of d: any two FP32 evaluations (MKL vs CUDA cores) pick different winners inside it
+    par = vq_oracle.classify_indices(idx_t[: 1 << 14], z[: 1 << 14], cb, rel_tol=1e-5)
+    assert par.mismatch == 0, par
