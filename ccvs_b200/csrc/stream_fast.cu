@@ -81,7 +81,10 @@ __device__ void fold_finalize(const StreamArgs& a, unsigned total_ctas, bool* s_
 // channel-major tiles
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int MAXIT>
-__global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : 4) cm4_kernel(const StreamArgs a, const Lay L, const int CS) {
+#ifndef CCVSQ_CM4_MINBLOCKS
+#define CCVSQ_CM4_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MINBLOCKS) cm4_kernel(const StreamArgs a, const Lay L, const int CS) {
   extern __shared__ float4 tile4[];                 // [FPT][CS/4], chunk index ^ (position/4)
   __shared__ float s_red[FNT / 32];
   __shared__ bool s_last;
@@ -258,7 +261,11 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : 4) cm4_kernel
       for (int j = 0; j < 4; ++j) {
         float4* dst = reinterpret_cast<float4*>(a.out + base[it] + (int64_t)j * L.S);
         const float4 v = *reinterpret_cast<const float4*>(oa[j]);
+#ifdef CCVSQ_STREAM_ALL_STORES
+        __stcs(dst, v);
+#else
         if (MODE == MODE_GATHER) __stcs(dst, v); else *dst = v;
+#endif
       }
     }
     if ((MODE == MODE_STATS || MODE == MODE_BACKWARD) && a.resid) {

@@ -247,9 +247,31 @@ class VectorQuantizer(nn.Module):
         """CUDA-graph the inference call for inputs of `z_static`'s shape (see GraphedQuantizer)."""
         return GraphedQuantizer(self, z_static, decode=decode)
 
-    def embed_code(self, code, channel_major_hw=None):
+    @torch.no_grad()
+    def fold_pointwise_head(self, head) -> torch.Tensor:
+        """Decoder head folded into the codebook (decoder side; inference only).
+
+        The decoder's first block is pointwise in space — `ConvLayer(z_size, block_in, 1)`: a 1x1 EqualConv2d and
+        FusedLeakyReLU (skip_autoencoder.py:368,428; gan.py:379-421) — and its input at a position is a codebook
+        row, so its output at that position is a function of the CODE alone.  `head` (any module or callable that
+        maps `[K, C, 1, 1] -> [K, C_out, 1, 1]`, e.g. the reference's `net_dec.blocks[0]`) is evaluated once on the
+        K codebook rows; `embed_code(code, channel_major_hw=(h, w), table=T)` then produces the head's output
+        `[G, C_out, h, w]` with the decode gather alone: no per-latent GEMM, no `[G, C, h, w]` intermediate.
+        Recompute the table whenever the codebook or the head's weights change."""
+        if self.mult != 1:
+            raise ValueError("fold_pointwise_head needs mult == 1 (with mult > 1 a position mixes several codes)")
+        w = self.embedding.weight
+        t = head(w.detach().view(self.n_e, self.e_dim, 1, 1))
+        if t.ndim != 4 or t.shape[0] != self.n_e or t.shape[2] != 1 or t.shape[3] != 1:
+            raise ValueError(f"head must map [K, C, 1, 1] to [K, C_out, 1, 1]; got {tuple(t.shape)}")
+        return t.reshape(self.n_e, -1).to(torch.float32).contiguous()
+
+    def embed_code(self, code, channel_major_hw=None, table=None):
         """E[code] (quantize.py:76-83).  `channel_major_hw=(h, w)` additionally fuses the caller's
-        NHWC->NCHW copy (quantized_video_model.py:833): code [G, h, w] -> [G, C, h, w]."""
+        NHWC->NCHW copy (quantized_video_model.py:833): code [G, h, w] -> [G, C, h, w].
+        `table` ([K, C_out] from `fold_pointwise_head`) gathers the folded decoder head instead of the codebook."""
+        if table is not None:
+            return self._embed_table(code, channel_major_hw, table)
         w = self.embedding.weight
         if not code.is_cuda:
             raise RuntimeError("CUDA only; there is no CPU fallback")
@@ -273,6 +295,29 @@ class VectorQuantizer(nn.Module):
                 z = z.view(s)
         self._last_gather_err = err   # device flag: nonzero if a code was outside [0, n_e)
         return z
+
+    def _embed_table(self, code, channel_major_hw, table):
+        if self.mult != 1:
+            raise ValueError("a folded head table needs mult == 1")
+        if not code.is_cuda or not table.is_cuda:
+            raise RuntimeError("CUDA only; there is no CPU fallback")
+        if table.ndim != 2 or table.shape[0] != self.n_e:
+            raise ValueError(f"table must be [n_e, C_out]; got {tuple(table.shape)}")
+        code = code.contiguous()
+        if code.dtype != torch.int64:
+            code = code.to(torch.int64)
+        flag = self._gather_flag(table.device)
+        c_out = table.shape[1]
+        if channel_major_hw is not None:
+            h, wd = channel_major_hw
+            S = h * wd
+            lay = Layout(code.numel() // S, c_out, S, 1)
+            out, err = ops.gather(code, table, lay, err=flag)
+            out = out.view(-1, c_out, h, wd)
+        else:
+            out, err = ops.gather(code, table, err=flag)
+        self._last_gather_err = err
+        return out
 
     def _gather_flag(self, dev) -> torch.Tensor:
         """Persistent device flag of embed_code (one int32, zeroed once): the gather kernels OR a 1 into it when a

@@ -503,3 +503,42 @@ def test_collapsed_codebook_every_row_falls_back():
     # sums is already 1e-6 of d: any two FP32 evaluations (MKL vs CUDA cores) pick different winners inside it
     par = vq_oracle.classify_indices(idx_t[: 1 << 14], z[: 1 << 14], cb, rel_tol=1e-5)
     assert par.mismatch == 0, par
+
+
+def test_decoder_head_folded_into_the_decode_gather():
+    """SURVEY 8f N3 (decoder side): embed_code + NHWC->NCHW + ConvLayer(z_size, block_in, 1) as ONE gather of a
+    K-row table.  Checked against the oracle's restatement of the reference chain (embedding -> transposes -> 1x1
+    equalised conv -> bias + LeakyReLU(0.2) * sqrt(2)) evaluated in FP32 on the CPU."""
+    torch.manual_seed(11)
+    K, C, C_out, G, h, w = 1024, 256, 512, 12, 16, 16
+    cb = torch.randn(K, C)
+    weight = torch.randn(C_out, C, 1, 1)
+    bias = 0.1 * torch.randn(C_out)
+    code = torch.randint(0, K, (G, h * w))
+    ref = vq_oracle.decoder_head(code, cb, weight, bias, (h, w))
+
+    vq = VectorQuantizer(K, C, 0.25).to(DEV).eval()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+    wd, bd = weight.to(DEV), bias.to(DEV)
+
+    def head(x):   # the reference's ConvLayer(C, C_out, 1) in plain torch ops (gan.py:108-115, fused_act.py:105-114)
+        out = torch.nn.functional.conv2d(x, wd * (1.0 / C ** 0.5))
+        return torch.nn.functional.leaky_relu(out + bd.view(1, -1, 1, 1), 0.2) * 2 ** 0.5
+
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False           # the table must be FP32 like the CPU oracle
+    try:
+        table = vq.fold_pointwise_head(head)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert table.shape == (K, C_out)
+    out = vq.embed_code(code.to(DEV), channel_major_hw=(h, w), table=table)
+    vq.check_codes()
+    assert out.shape == (G, C_out, h, w)
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+    # the gather itself is exact: every position carries its code's table row bit for bit
+    assert torch.equal(out.permute(0, 2, 3, 1).reshape(-1, C_out), table[code.view(-1).to(DEV)])
+    # channel-last variant ([G, h*w, C_out])
+    out_cl = vq.embed_code(code.to(DEV), table=table)
+    assert torch.equal(out_cl.view(-1, C_out), table[code.view(-1).to(DEV)])

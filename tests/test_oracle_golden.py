@@ -120,3 +120,16 @@ def test_oracle_polyak_and_embed_tokens_shapes():
     tok, pos = torch.arange(12.).view(4, 3), torch.ones(1, 5, 3)
     e = vq_oracle.embed_tokens(torch.tensor([[0, 3], [1, 1]]), tok, pos)
     assert e.shape == (2, 2, 3) and torch.equal(e[0, 1], tok[3] + 1)
+
+
+def test_oracle_decoder_head_is_a_function_of_the_code():
+    """The property the folded decoder head relies on: the reference chain embed_code -> transposes -> 1x1 conv ->
+    bias + LeakyReLU (vq_oracle.decoder_head) gives, at every position, the same vector as the chain applied to the
+    single codebook row of that position's code."""
+    torch.manual_seed(3)
+    K, C, C_out, G, h, w = 64, 32, 48, 3, 4, 5
+    cb, weight, bias = torch.randn(K, C), torch.randn(C_out, C, 1, 1), torch.randn(C_out)
+    code = torch.randint(0, K, (G, h * w))
+    full = vq_oracle.decoder_head(code, cb, weight, bias, (h, w))                      # [G, C_out, h, w]
+    per_code = vq_oracle.decoder_head(torch.arange(K).view(K, 1), cb, weight, bias, (1, 1)).view(K, C_out)
+    torch.testing.assert_close(full.permute(0, 2, 3, 1).reshape(-1, C_out), per_code[code.view(-1)], rtol=1e-6, atol=1e-6)
