@@ -300,7 +300,7 @@ def main():
         _, sq, counts = ops.assign(zd, lay, w, idx)
         ops.finalize(K, D, float(zd.numel()), float(n_lat), 0.25, counts=counts, sq_err=sq, want_loss=True, want_perplexity=True)
         if train:
-            ops.timed("ccvsq_quantize_backward", lambda: ops.quantize_backward(zd, lay, w, idx, g_out, g_one, 0.25))
+            ops.quantize_backward(zd, lay, w, idx, g_out, g_one, 0.25)   # (the C call itself is bracketed by events)
             resid, _ = ops.code_stats(zd, lay, w, K, idx, sub=1.0, want_counts=False)
             ops.ema_update(w.clone(), vq.ema_count.clone(), vq.ema_sum.clone(), resid, counts, 0.99, 1e-5)
         else:

@@ -26,10 +26,12 @@ constexpr int FPT = 32;    // positions per tile
 constexpr int FNT = 256;   // threads per CTA
 constexpr int FSLAB = 256; // channels per CTA (a tile is FPT x slab)
 
-// 16-byte global -> shared copy that bypasses the register file (LDGSTS, L2-only caching: codebook rows are
-// scattered, a line is rarely reused by the same SM)
+// 16-byte global -> shared copy that bypasses the register file (LDGSTS).  Cached in L1 as well (.ca): with a
+// skewed code distribution (codebook collapse: most latents on a few codes) every SM keeps asking for the same few
+// lines, and L2-only caching (.cg) serialises all of them on the L2 slices that own those lines (measured: 12x
+// slower when all latents share one code).
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -209,11 +211,19 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
     }
   }
   if (a.counts && blockIdx.y == 0 && (MODE == MODE_ASSIGN || MODE == MODE_STATS)) {
+    // usage counts: equal codes inside a warp are combined first (one atomic per distinct code; a collapsed
+    // codebook would otherwise put every latent's atomic on the same address)
     const int rows = np * L.mult;
-    for (int r = tid; r < rows; r += FNT) {
-      int64_t k = __ldg(a.idx + p0 * L.mult + r);
-      if (MODE == MODE_ASSIGN) k = k < 0 ? 0 : (k >= a.K ? a.K - 1 : k);
-      if (k >= 0 && k < a.K) atomicAdd(a.counts + k, 1);
+    for (int r0 = tid & ~31; r0 < rows; r0 += FNT) {            // warp-uniform trip count
+      const int r = r0 + (tid & 31);
+      int64_t k = -1;
+      if (r < rows) {
+        k = __ldg(a.idx + p0 * L.mult + r);
+        if (MODE == MODE_ASSIGN) k = k < 0 ? 0 : (k >= a.K ? a.K - 1 : k);
+        if (k < 0 || k >= a.K) k = -1;
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
+      if (k >= 0 && (tid & 31) == __ffs(peers) - 1) atomicAdd(a.counts + k, __popc(peers));
     }
   }
   cp_async_wait_all();

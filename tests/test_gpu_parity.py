@@ -542,3 +542,28 @@ def test_decoder_head_folded_into_the_decode_gather():
     # channel-last variant ([G, h*w, C_out])
     out_cl = vq.embed_code(code.to(DEV), table=table)
     assert torch.equal(out_cl.view(-1, C_out), table[code.view(-1).to(DEV)])
+
+
+@pytest.mark.parametrize("shape", [(6, 256, 16, 16), (3, 64, 5, 8), (700, 128)])
+def test_assign_with_skewed_code_usage(shape):
+    """Codebook collapse: most latents on one or two codes (the usage counts combine equal codes per warp before the
+    atomics, and the codebook-row gather must not depend on rows being distinct)."""
+    torch.manual_seed(17)
+    D = shape[1] if len(shape) > 2 else shape[-1]
+    K = 37
+    z = torch.randn(shape, device=DEV)
+    cb = torch.randn(K, D, device=DEV)
+    lay = ops.layout_of(shape, D, 1)
+    N = lay.rows
+    for idx in (torch.zeros(N, dtype=torch.int64, device=DEV),
+                torch.where(torch.rand(N, device=DEV) < 0.9, 5, 31).to(torch.int64),
+                torch.randint(0, K, (N,), device=DEV)):
+        zq, sq, counts = ops.assign(z, lay, cb, idx)
+        assert torch.equal(counts.to(torch.int64), torch.bincount(idx, minlength=K))
+        rows = vq_oracle.to_channel_last(z.cpu()).reshape(-1, D) if len(shape) >= 4 else z.cpu().reshape(-1, D)
+        e = cb.cpu()[idx.cpu()]
+        ref = rows + (e - rows)
+        ours = vq_oracle.to_channel_last(zq.cpu()).reshape(-1, D) if len(shape) >= 4 else zq.cpu().reshape(-1, D)
+        assert torch.equal(ours, ref)
+        ref_sq = float(((e - rows).double() ** 2).sum())
+        assert abs(float(sq) - ref_sq) <= 1e-5 * ref_sq
