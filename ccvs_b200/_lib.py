@@ -51,6 +51,7 @@ class ForwardArgs(Structure):
         ("header", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_uint64),
         ("idx", c_void_p), ("zq", c_void_p), ("loss", c_void_p), ("perplexity", c_void_p),
         ("ev_search_begin", c_void_p), ("ev_search_end", c_void_p),
+        ("resid", c_void_p),
     ]
 
 

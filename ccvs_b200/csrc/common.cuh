@@ -102,7 +102,9 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // HBM-bound stream kernels: argument block shared by the generic (stream_kernels.cu) and the
 // 128-bit fast paths (stream_fast.cu)
 // ---------------------------------------------------------------------------------------------
-enum { MODE_ASSIGN = 0, MODE_BACKWARD = 1, MODE_GATHER = 2, MODE_STATS = 3 };
+enum { MODE_ASSIGN = 0, MODE_BACKWARD = 1, MODE_GATHER = 2, MODE_STATS = 3,
+       MODE_ASSIGN_STATS = 4 };   // assign with the per-code residual sums on the same pass (internal to the fast kernels)
+#define IS_ASSIGN(MODE) ((MODE) == MODE_ASSIGN || (MODE) == MODE_ASSIGN_STATS)
 
 struct FinArgs {          // loss / perplexity folded into the assign kernel (last CTA); ticket NULL = off
   int32_t* ticket;        // zeroed by the caller

@@ -117,6 +117,11 @@ extern "C" int ccvsq_quantize_forward(const ccvsq_forward_args* a, void* stream)
   s.fin.M = (double)L.P * L.C;
   s.fin.N = (double)L.N;
   s.fin.beta = a->beta;
+  if (a->resid) {   // per-code residual sums on the same pass (EMA codebook update)
+    CCVSQ_CUDA(cudaMemsetAsync(a->resid, 0, (size_t)K * D * sizeof(float), st));
+    s.resid = a->resid;
+    s.sub = 1.f;
+  }
   return stream_launch(MODE_ASSIGN, s, L, st);
 }
 

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
   #ifdef CCVSQ_ASSIGN_FORWARD_ORDER
   const uint32_t bx = blockIdx.x;
 #else
-  const uint32_t bx = MODE == MODE_ASSIGN ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const uint32_t bx = IS_ASSIGN(MODE) ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
 #endif
   const int64_t p0 = (int64_t)bx * FPT;
   const int np = (int)min((int64_t)FPT, L.P - p0);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
   // CTA goes idx -> codebook rows -> compute -> store, and only 4 CTAs fit an SM)
   if (tile_in_group) {
     const int64_t ahead = (int64_t)CCVSQ_PREFETCH_WAVES * kNumSMs * (MODE == MODE_BACKWARD ? 2 : 4);
-    const int64_t nb = MODE == MODE_ASSIGN ? (int64_t)bx - ahead : (int64_t)bx + ahead;
+    const int64_t nb = IS_ASSIGN(MODE) ? (int64_t)bx - ahead : (int64_t)bx + ahead;
     if (nb >= 0 && nb < (int64_t)gridDim.x) {
       const uint32_t tpg = (uint32_t)L.S >> 5;
       const uint32_t g = (uint32_t)nb / tpg;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
       }
     }
   }
-  if (a.counts && blockIdx.y == 0 && (MODE == MODE_ASSIGN || MODE == MODE_STATS)) {
+  if (a.counts && blockIdx.y == 0 && (IS_ASSIGN(MODE) || MODE == MODE_STATS)) {
     // usage counts: equal codes inside a warp are combined first (one atomic per distinct code; a collapsed
     // codebook would otherwise put every latent's atomic on the same address)
     const int rows = np * L.mult;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
       int64_t k = -1;
       if (r < rows) {
         k = __ldg(a.idx + p0 * L.mult + r);
-        if (MODE == MODE_ASSIGN) k = k < 0 ? 0 : (k >= a.K ? a.K - 1 : k);
+        if (IS_ASSIGN(MODE)) k = k < 0 ? 0 : (k >= a.K ? a.K - 1 : k);
         if (k < 0 || k >= a.K) k = -1;
       }
       const unsigned peers = __match_any_sync(0xffffffffu, (unsigned long long)k);
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
       for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(ea[i]) = tile4[(4 * p4 + i) * QS + (cq ^ p4)];
     }
     float oa[4][4];                                 // [channel j][position i]
-    if (MODE == MODE_ASSIGN) {
+    if (IS_ASSIGN(MODE)) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -278,11 +278,11 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
 #endif
       }
     }
-    if ((MODE == MODE_STATS || MODE == MODE_BACKWARD) && a.resid) {
+    if ((MODE == MODE_STATS || MODE == MODE_BACKWARD || MODE == MODE_ASSIGN_STATS) && a.resid) {
       const int c = c_lo + 4 * cq;
       const int m = L.mult == 1 ? 0 : c / L.D;
       const int j0 = c - m * L.D;
-      const float sub = MODE == MODE_BACKWARD ? 1.f : a.sub;
+      const float sub = MODE == MODE_STATS ? a.sub : 1.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int64_t k = __ldg(a.idx + (p0 + 4 * p4 + i) * L.mult + m);
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
     }
   }
 
-  if (MODE == MODE_ASSIGN && a.sq_err) {
+  if (IS_ASSIGN(MODE) && a.sq_err) {
     acc = warp_sum(acc);
     if ((tid & 31) == 0) s_red[tid >> 5] = acc;
     __syncthreads();
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
       atomicAdd(a.sq_err, (double)s);
     }
   }
-  if (MODE == MODE_ASSIGN && a.fin.ticket) fold_finalize(a, gridDim.x * gridDim.y, &s_last, s_red);
+  if (IS_ASSIGN(MODE) && a.fin.ticket) fold_finalize(a, gridDim.x * gridDim.y, &s_last, s_red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(FNT) rows4_kernel(const StreamArgs a, const in
     if (has_g) *reinterpret_cast<float4*>(g) = gv[u];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (MODE == MODE_ASSIGN) {
+      if (IS_ASSIGN(MODE)) {
         const float diff = __fsub_rn(e[j], x[j]);
         out[j] = __fadd_rn(x[j], diff);
         acc = fmaf(diff, diff, acc);
@@ -390,16 +390,16 @@ __global__ void __launch_bounds__(FNT) rows4_kernel(const StreamArgs a, const in
       const float4 v = *reinterpret_cast<const float4*>(out);
       if (MODE == MODE_GATHER) __stcs(dst, v); else *dst = v;
     }
-    if ((MODE == MODE_STATS || MODE == MODE_BACKWARD) && a.resid) {
-      const float sub = MODE == MODE_BACKWARD ? 1.f : a.sub;
+    if ((MODE == MODE_STATS || MODE == MODE_BACKWARD || MODE == MODE_ASSIGN_STATS) && a.resid) {
+      const float sub = MODE == MODE_STATS ? a.sub : 1.f;
       float r[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) r[j] = need_e ? x[j] - sub * e[j] : x[j];
       red_add_v4(a.resid + (size_t)k[u] * D + 4 * q[u], r[0], r[1], r[2], r[3]);
     }
-    if (a.counts && q[u] == 0 && (MODE == MODE_ASSIGN || MODE == MODE_STATS)) atomicAdd(a.counts + k[u], 1);
+    if (a.counts && q[u] == 0 && (IS_ASSIGN(MODE) || MODE == MODE_STATS)) atomicAdd(a.counts + k[u], 1);
   }
-  if (MODE == MODE_ASSIGN && a.sq_err) {
+  if (IS_ASSIGN(MODE) && a.sq_err) {
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
     __syncthreads();
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(FNT) rows4_kernel(const StreamArgs a, const in
       atomicAdd(a.sq_err, (double)s);
     }
   }
-  if (MODE == MODE_ASSIGN && a.fin.ticket) fold_finalize(a, gridDim.x, &s_last, s_red);
+  if (IS_ASSIGN(MODE) && a.fin.ticket) fold_finalize(a, gridDim.x, &s_last, s_red);
 }
 
 // Row-major, D % 128 == 0: one warp per RPW consecutive rows, lanes over the chunks of a row.  No
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kern
       else kk = kk < 0 ? 0 : a.K - 1;
     }
     k[i] = kk;
-    if (a.counts && valid[i] && lane == 0 && (MODE == MODE_ASSIGN || MODE == MODE_STATS)) atomicAdd(a.counts + kk, 1);
+    if (a.counts && valid[i] && lane == 0 && (IS_ASSIGN(MODE) || MODE == MODE_STATS)) atomicAdd(a.counts + kk, 1);
   }
   float coef = 0.f;
   if (MODE == MODE_BACKWARD) coef = __ldg(a.g_loss) * a.coef_scale;
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kern
       if (has_g) *reinterpret_cast<float4*>(g) = gv[i];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        if (MODE == MODE_ASSIGN) {
+        if (IS_ASSIGN(MODE)) {
           const float diff = __fsub_rn(e[t], x[t]);
           out[t] = __fadd_rn(x[t], diff);
           acc = fmaf(diff, diff, acc);
@@ -486,8 +486,8 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kern
         const float4 v = *reinterpret_cast<const float4*>(out);
         if (MODE == MODE_GATHER) __stcs(dst, v); else *dst = v;
       }
-      if ((MODE == MODE_STATS || MODE == MODE_BACKWARD) && a.resid) {
-        const float sub = MODE == MODE_BACKWARD ? 1.f : a.sub;
+      if ((MODE == MODE_STATS || MODE == MODE_BACKWARD || MODE == MODE_ASSIGN_STATS) && a.resid) {
+        const float sub = MODE == MODE_STATS ? a.sub : 1.f;
         float r[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) r[t] = need_e ? x[t] - sub * e[t] : x[t];
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kern
       }
     }
   }
-  if (MODE == MODE_ASSIGN && a.sq_err) {
+  if (IS_ASSIGN(MODE) && a.sq_err) {
     acc = warp_sum(acc);
     if (lane == 0) s_red[threadIdx.x >> 5] = acc;
     __syncthreads();
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kern
       atomicAdd(a.sq_err, (double)s);
     }
   }
-  if (MODE == MODE_ASSIGN && a.fin.ticket) fold_finalize(a, gridDim.x, &s_last, s_red);
+  if (IS_ASSIGN(MODE) && a.fin.ticket) fold_finalize(a, gridDim.x, &s_last, s_red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -560,7 +560,9 @@ static int launch_rows4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
 int stream_fast_launch(int mode, const StreamArgs& a, const Lay& L, cudaStream_t st) {
   const bool cm = L.S > 1;
   switch (mode) {
-    case MODE_ASSIGN:   return cm ? launch_cm4<MODE_ASSIGN>(a, L, st) : launch_rows4<MODE_ASSIGN>(a, L, st);
+    case MODE_ASSIGN:
+      if (a.resid) return cm ? launch_cm4<MODE_ASSIGN_STATS>(a, L, st) : launch_rows4<MODE_ASSIGN_STATS>(a, L, st);
+      return cm ? launch_cm4<MODE_ASSIGN>(a, L, st) : launch_rows4<MODE_ASSIGN>(a, L, st);
     case MODE_BACKWARD: return cm ? launch_cm4<MODE_BACKWARD>(a, L, st) : launch_rows4<MODE_BACKWARD>(a, L, st);
     case MODE_GATHER:   return cm ? launch_cm4<MODE_GATHER>(a, L, st) : launch_rows4<MODE_GATHER>(a, L, st);
     case MODE_STATS:    return cm ? launch_cm4<MODE_STATS>(a, L, st) : launch_rows4<MODE_STATS>(a, L, st);

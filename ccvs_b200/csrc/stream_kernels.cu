@@ -515,6 +515,11 @@ int stream_launch(int mode, const StreamArgs& a, const Lay& L, cudaStream_t st) 
     case MODE_ASSIGN:
       if (int rc = enable_smem(assign_kernel, smem)) return rc;
       assign_kernel<<<tiles, NT, smem, st>>>(a.x, L, a.E, a.K, a.idx, a.out, a.sq_err, a.counts);
+      if (a.resid) {   // generic layouts: the per-code residual sums take their own pass
+        CCVSQ_LAUNCH_CHECK();
+        if (int rc = enable_smem(code_stats_kernel, smem)) return rc;
+        code_stats_kernel<<<tiles, NT, smem, st>>>(a.x, L, a.E, a.K, a.idx, 1.f, a.resid, nullptr);
+      }
       break;
     case MODE_BACKWARD:
       if (a.out) {

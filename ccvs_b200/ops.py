@@ -416,11 +416,12 @@ class ForwardOut:
     loss: Optional[torch.Tensor]          # 0-d fp32
     perplexity: Optional[torch.Tensor]    # 0-d fp32
     counts: Optional[torch.Tensor]        # int32 [K]
+    resid: Optional[torch.Tensor] = None  # fp32 [K, D]: sum_{idx=k} (z - E[k]) (want_resid)
 
 
 def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: float, mode: str = "auto", n_cand: int = 4,
                      margin_tau: float = 1.0, exact_fallback: bool = True, cb: Optional[PreparedCodebook] = None,
-                     indices_only: bool = False) -> ForwardOut:
+                     indices_only: bool = False, want_resid: bool = False) -> ForwardOut:
     """The whole forward of quantize.py:32-74 in one call of the C ABI (ccvsq_quantize_forward).
     `cb` = cached codebook side data (frozen codebook); None rebuilds it inside the call."""
     _req(z, torch.float32, "z")
@@ -453,8 +454,12 @@ def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: f
         a.e_max = cb.e_max.data_ptr() if cb.e_max is not None else None
     a.header, a.workspace, a.workspace_bytes = hdr.data_ptr(), ws.data_ptr(), ws_bytes
     a.idx = idx.data_ptr()
+    resid = None
     if not indices_only:
         a.zq, a.loss, a.perplexity = zq.data_ptr(), loss.data_ptr(), perp.data_ptr()
+        if want_resid:
+            resid = torch.empty(K, D, dtype=torch.float32, device=dev)
+            a.resid = resid.data_ptr()
     name = "ccvsq_screen" if tensor else "ccvsq_search_exact"
     timed = PROFILER.timing is True or (PROFILER.timing and name in PROFILER.timing)
     if timed:   # the dominant search kernel is bracketed by events recorded inside the C call
@@ -470,7 +475,7 @@ def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: f
         n += 1 if fast_stream_layout(lay) else 2
     PROFILER.launches += n
     counts = None if indices_only else hdr[_lib.HEADER_INTS:]
-    return ForwardOut(idx, zq, loss, perp, counts)
+    return ForwardOut(idx, zq, loss, perp, counts, resid)
 
 
 def quantize_backward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, idx: torch.Tensor,

@@ -69,8 +69,10 @@ class _QuantizeFn(torch.autograd.Function):
     def forward(ctx, z, weight, module):
         lay = ops.layout_of(z.shape, module.e_dim, module.mult)
         out = ops.quantize_forward(z, lay, weight, module.beta, module.search_mode, module.n_cand, module.margin_tau,
-                                   module.exact_fallback, cb=module._cb_cached())
+                                   module.exact_fallback, cb=module._cb_cached(),
+                                   want_resid=getattr(module, "_want_resid", False))
         zq, loss, idx, perp, counts = out.zq, out.loss, out.idx, out.perplexity, out.counts
+        module._last_resid = out.resid        # per-code residual sums for the EMA update (None unless asked for)
         ctx.lay = lay
         ctx.beta = module.beta
         # the EMA variant rewrites the codebook in place right after forward: keep the version the
@@ -404,17 +406,20 @@ class EMAVectorQuantizer(VectorQuantizer):
         self.register_buffer("ema_sum", self.embedding.weight.detach().clone())
 
     def forward(self, z):
-        out = super().forward(z)
+        # the per-code residual sums of the EMA update ride on the assign pass of the forward (one read of z)
+        self._want_resid = self.training
+        try:
+            out = super().forward(z)
+        finally:
+            self._want_resid = False
         if self.training:
             with torch.no_grad():
-                zc = z.detach().contiguous()
                 w = self.embedding.weight
-                lay = ops.layout_of(zc.shape, self.e_dim, self.mult)
-                idx = out[2][2].view(-1)
-                resid, _ = ops.code_stats(zc, lay, w, self.n_e, idx, sub=1.0, want_counts=False)
+                resid = self._last_resid
+                self._last_resid = None
                 counts = self.last_counts          # per-code usage from the forward's assign kernel
                 if self.sync:
-                    sq = torch.zeros(1, dtype=torch.float64, device=zc.device)
+                    sq = torch.zeros(1, dtype=torch.float64, device=resid.device)
                     resid, counts, _ = vq_dist.all_reduce_stats(resid, counts, sq)
                     resid = resid.contiguous()
                 ops.ema_update(w, self.ema_count, self.ema_sum, resid, counts, self.decay, self.eps)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CCVSQ_VERSION 102 /* major*100 + minor */
+#define CCVSQ_VERSION 103 /* major*100 + minor */
 
 typedef enum ccvsq_status {
   CCVSQ_OK = 0,
@@ -260,6 +260,9 @@ typedef struct ccvsq_forward_args {
   float* perplexity;
   void* ev_search_begin;
   void* ev_search_end;
+  float* resid;            /* optional [K, D] (zeroed by the call): resid[k,:] = sum_{idx=k} (z - E[k]), the per-code
+                              statistic of an EMA codebook update, accumulated by the assign pass on its own read of z
+                              (no second pass over the latents); NULL = off */
 } ccvsq_forward_args;
 
 uint64_t ccvsq_forward_workspace_bytes(int64_t N, int K, int D, int search_mode, int n_cand,

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_version():
-    assert _lib.load().ccvsq_version() == 102
+    assert _lib.load().ccvsq_version() == 103
 
 
 def test_argument_validation_without_gpu():
@@ -78,7 +78,8 @@ def test_composite_argument_validation_without_gpu():
 
 
 def test_layout_struct_matches_header():
-    assert ctypes.sizeof(_lib.ForwardArgs) == 168
+    assert ctypes.sizeof(_lib.ForwardArgs) == 176
+    assert _lib.ForwardArgs.resid.offset == 168
     assert _lib.ForwardArgs.lay.offset == 8 and _lib.ForwardArgs.e_sq.offset == 72 and _lib.ForwardArgs.idx.offset == 120
     assert ctypes.sizeof(_lib.Layout) == 24     # int64 + 3 x int32 (+4 pad)
     assert _lib.Layout.G.offset == 0 and _lib.Layout.C.offset == 8 and _lib.Layout.mult.offset == 16

@@ -567,3 +567,24 @@ def test_assign_with_skewed_code_usage(shape):
         assert torch.equal(ours, ref)
         ref_sq = float(((e - rows).double() ** 2).sum())
         assert abs(float(sq) - ref_sq) <= 1e-5 * ref_sq
+
+
+@pytest.mark.parametrize("shape,K,D", [((8, 256, 16, 16), 1024, 256), ((3, 64, 5, 7), 200, 64), ((300, 128), 96, 128)])
+def test_forward_with_fused_code_statistics(shape, K, D):
+    """ccvsq_forward_args.resid: the per-code residual sums of the EMA update accumulated by the assign pass equal
+    the stand-alone scatter-reduce (ccvsq_code_stats) and the oracle's sum_{idx=k} (z - E[k]); everything else
+    the forward returns is unchanged."""
+    z, cb = vq_oracle.synth(shape, K, D, "T", seed=99)
+    zd, cbd = z.to(DEV), cb.to(DEV)
+    lay = ops.layout_of(shape, D, 1)
+    plain = ops.quantize_forward(zd, lay, cbd, 0.25)
+    fused = ops.quantize_forward(zd, lay, cbd, 0.25, want_resid=True)
+    assert torch.equal(plain.idx, fused.idx) and torch.equal(plain.zq, fused.zq)
+    assert torch.equal(plain.counts, fused.counts)
+    torch.testing.assert_close(fused.loss, plain.loss, rtol=1e-6, atol=0)
+    alone, _ = ops.code_stats(zd, lay, cbd, K, plain.idx, sub=1.0, want_counts=False)
+    torch.testing.assert_close(fused.resid, alone, rtol=1e-4, atol=1e-4)
+    rows = (vq_oracle.to_channel_last(z) if len(shape) >= 4 else z).reshape(-1, D).double()
+    idx = plain.idx.cpu()
+    ref = torch.zeros(K, D, dtype=torch.float64).index_add_(0, idx, rows - cb.double()[idx])
+    torch.testing.assert_close(fused.resid.cpu().double(), ref, rtol=1e-4, atol=1e-4)
