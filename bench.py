@@ -119,6 +119,17 @@ def make_inputs(workload: str, device, seed: int):
     return z, cb, n
 
 
+def use_all_host_threads() -> int:
+    """The CPU legs run on every host core this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which would silently time the reference on ONE thread: override it explicitly."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference(args):
     """The reference's own CPU path (oracle port, torch-CPU FP32, all host threads) on a bounded
     sample of the workload.  Rank 0 only."""
@@ -135,7 +146,7 @@ def run_reference(args):
         sample_frames = max(1, min(sample_frames, 4096 // (h * w)))
     z, cb = vq_oracle.synth((sample_frames, D, h, w), K, D, "T", seed=1234)
     n = sample_frames * h * w
-    threads = torch.get_num_threads()
+    threads = use_all_host_threads()
 
     def step():
         with torch.no_grad():
@@ -164,6 +175,7 @@ def cpu_baseline(workload: str, budget_s: float = 10.0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import vq_oracle
     (clips, frames), D, h, w, K, _ = WORKLOADS[workload]
+    use_all_host_threads()
     sample_frames = max(1, min(clips * frames, (16384 if K < 16384 else 4096) // (h * w)))
     z, cb = vq_oracle.synth((sample_frames, D, h, w), K, D, "T", seed=1234)
     n = sample_frames * h * w

@@ -60,6 +60,23 @@ def all_reduce_stats(resid: torch.Tensor, counts: torch.Tensor, sq_err: torch.Te
     return unpack_stats(buf, K, D)
 
 
+def ema_stats_buffer(K: int, D: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Packed buffer for the EMA statistics exchange, [resid: K*D | counts: K] fp32, and the [K, D] view the assign
+    pass accumulates the residual sums into directly (no pack copy)."""
+    buf = torch.empty(K * D + K, dtype=torch.float32, device=device)
+    return buf, buf[: K * D].view(K, D)
+
+
+def reduce_ema_stats(buf: torch.Tensor, counts: torch.Tensor, K: int, D: int,
+                     group: Optional[dist.ProcessGroup] = None):
+    """`buf[:K*D]` already holds this rank's residual sums; the usage counts join it (exact in fp32 below 2^24 per
+    code) and ONE all-reduce sums both over the ranks.  Returns (resid [K, D] view, counts int32 [K])."""
+    buf[K * D:].copy_(counts)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf[: K * D].view(K, D), buf[K * D:].round().to(torch.int32)
+
+
 def world_info(group: Optional[dist.ProcessGroup] = None) -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)

@@ -421,7 +421,8 @@ class ForwardOut:
 
 def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: float, mode: str = "auto", n_cand: int = 4,
                      margin_tau: float = 1.0, exact_fallback: bool = True, cb: Optional[PreparedCodebook] = None,
-                     indices_only: bool = False, want_resid: bool = False) -> ForwardOut:
+                     indices_only: bool = False, want_resid: bool = False,
+                     resid_out: Optional[torch.Tensor] = None) -> ForwardOut:
     """The whole forward of quantize.py:32-74 in one call of the C ABI (ccvsq_quantize_forward).
     `cb` = cached codebook side data (frozen codebook); None rebuilds it inside the call."""
     _req(z, torch.float32, "z")
@@ -457,7 +458,12 @@ def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: f
     resid = None
     if not indices_only:
         a.zq, a.loss, a.perplexity = zq.data_ptr(), loss.data_ptr(), perp.data_ptr()
-        if want_resid:
+        if resid_out is not None:          # caller's buffer (e.g. a view of the packed all-reduce buffer)
+            resid = _req(resid_out, torch.float32, "resid_out")
+            if tuple(resid.shape) != (K, D):
+                raise ValueError(f"resid_out must be [{K}, {D}]; got {tuple(resid.shape)}")
+            a.resid = resid.data_ptr()
+        elif want_resid:
             resid = torch.empty(K, D, dtype=torch.float32, device=dev)
             a.resid = resid.data_ptr()
     name = "ccvsq_screen" if tensor else "ccvsq_search_exact"

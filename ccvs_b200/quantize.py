@@ -70,7 +70,8 @@ class _QuantizeFn(torch.autograd.Function):
         lay = ops.layout_of(z.shape, module.e_dim, module.mult)
         out = ops.quantize_forward(z, lay, weight, module.beta, module.search_mode, module.n_cand, module.margin_tau,
                                    module.exact_fallback, cb=module._cb_cached(),
-                                   want_resid=getattr(module, "_want_resid", False))
+                                   want_resid=getattr(module, "_want_resid", False),
+                                   resid_out=getattr(module, "_resid_out", None))
         zq, loss, idx, perp, counts = out.zq, out.loss, out.idx, out.perplexity, out.counts
         module._last_resid = out.resid        # per-code residual sums for the EMA update (None unless asked for)
         ctx.lay = lay
@@ -406,21 +407,24 @@ class EMAVectorQuantizer(VectorQuantizer):
         self.register_buffer("ema_sum", self.embedding.weight.detach().clone())
 
     def forward(self, z):
-        # the per-code residual sums of the EMA update ride on the assign pass of the forward (one read of z)
+        # the per-code residual sums of the EMA update ride on the assign pass of the forward (one read of z); with
+        # several ranks they are accumulated straight into the packed buffer of the one all-reduce
+        buf = None
         self._want_resid = self.training
+        if self.training and self.sync and vq_dist.world_info()[1] > 1:
+            buf, self._resid_out = vq_dist.ema_stats_buffer(self.n_e, self.e_dim, z.device)
         try:
             out = super().forward(z)
         finally:
             self._want_resid = False
+            self._resid_out = None
         if self.training:
             with torch.no_grad():
                 w = self.embedding.weight
                 resid = self._last_resid
                 self._last_resid = None
                 counts = self.last_counts          # per-code usage from the forward's assign kernel
-                if self.sync:
-                    sq = torch.zeros(1, dtype=torch.float64, device=resid.device)
-                    resid, counts, _ = vq_dist.all_reduce_stats(resid, counts, sq)
-                    resid = resid.contiguous()
+                if buf is not None:
+                    resid, counts = vq_dist.reduce_ema_stats(buf, counts, self.n_e, self.e_dim)
                 ops.ema_update(w, self.ema_count, self.ema_sum, resid, counts, self.decay, self.eps)
         return out

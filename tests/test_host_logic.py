@@ -135,3 +135,43 @@ def test_sharded_statistics_equal_global_gloo():
     perp = torch.exp(-(p * torch.log(p + 1e-10)).sum())
     torch.testing.assert_close(perp, res.perplexity, rtol=1e-5, atol=0)
     assert int(counts.sum()) == N
+
+
+def _ema_stats_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        K, D = 32, 16
+        z, cb = vq_oracle.synth((8, 16, 4, 4), K, D, "T", seed=5)
+        a, b = vqd.frame_shard(z.shape[0], rank, world)
+        rows = vq_oracle.to_channel_last(z[a:b]).reshape(-1, D)
+        idx = vq_oracle.nearest(rows, cb)
+        buf, resid_view = vqd.ema_stats_buffer(K, D, "cpu")
+        resid_view.zero_().index_add_(0, idx, rows - cb[idx])       # what the assign pass accumulates in place
+        counts = torch.bincount(idx, minlength=K).to(torch.int32)
+        resid, counts = vqd.reduce_ema_stats(buf, counts, K, D)
+        if rank == 0:
+            ret.put((resid.clone(), counts.clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ema_statistics_one_all_reduce_gloo():
+    """2 ranks: residual sums accumulated straight into the packed buffer + counts, ONE all-reduce; the result equals
+    the statistics of the whole batch and drives the textbook EMA update to the same codebook."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ema_stats_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    resid, counts = ret.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    K, D = 32, 16
+    z, cb = vq_oracle.synth((8, 16, 4, 4), K, D, "T", seed=5)
+    rows = vq_oracle.to_channel_last(z).reshape(-1, D)
+    idx = vq_oracle.nearest(rows, cb)
+    assert counts.dtype == torch.int32 and torch.equal(counts.long(), torch.bincount(idx, minlength=K))
+    torch.testing.assert_close(resid, torch.zeros(K, D).index_add_(0, idx, rows - cb[idx]), rtol=1e-5, atol=1e-5)
