@@ -42,6 +42,7 @@ WORKLOADS = {
     "c4": ((2048, 16), 256, 8, 8, 16384, "large-codebook stress shard, 2^21 latents, K=16384, D=256"),
     "train": ((64, 16), 256, 16, 16, 1024, "training-mode quantizer (fwd+bwd+EMA update), c2 shape"),
 }
+print_result = print      # replaced in main(): writes to the process's original stdout
 METRIC = "latents_quantized_per_sec"
 UNIT = "latents/s"
 
@@ -161,7 +162,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     val = n / dt
     sample = f"{n} latents ({sample_frames} frames x {h}x{w}) per step, dense N x K algorithm, distribution T"
-    print(json.dumps({
+    print_result(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -208,6 +209,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) goes to
+    # stderr instead — fd 1 is pointed at fd 2 for the run and the result is written to the saved descriptor
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+    result_out = os.fdopen(result_fd, "w")
+    global print_result
+    def print_result(line: str):
+        result_out.write(line + "\n")
+        result_out.flush()
 
     if args.impl == "reference":
         run_reference(args)
@@ -473,7 +485,7 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "kernel_breakdown": breakdown, "hbm_kernels": extra, "small_batch": small,
     }
-    print(json.dumps(line))
+    print_result(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
   __shared__ int64_t row_id[XR];
 
   const int64_t total_rows = row_list ? min((int64_t)row_count[0], max_rows) : L.N;
+  if (row_list && total_rows == 0) return;   // the usual case of the fallback launch: nothing was flagged (every CTA
+                                             // sees the same count, so the ticket below is skipped consistently)
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   // this CTA's slice of the codebook (whole codebook when gridDim.y == 1), aligned to the slab width
