@@ -1,6 +1,7 @@
 // api.cu — version / error-string plumbing of the C ABI (include/ccvsq.h).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <mutex>
 #include "common.cuh"
 
@@ -36,6 +37,10 @@ int enable_smem_impl(const void* kern, size_t bytes) {
   if (!slot && g_num_grants < 128) slot = &g_grants[g_num_grants++];
   if (slot) { slot->kern = kern; slot->dev = dev; slot->bytes = bytes; }
   return CCVSQ_OK;
+}
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CCVSQ_NO_PDL"); return !(e && atoi(e) != 0); }();
+  return on;
 }
 }  // namespace ccvsq
 

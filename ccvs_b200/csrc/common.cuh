@@ -91,6 +91,35 @@ inline int enable_smem(Kern kern, size_t bytes) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): the kernels of one forward run back to back on one stream and each
+// boundary costs a few microseconds of launch latency + prologue — a quarter of the whole call at the 1k-5k
+// latents the reference trainer issues.  Every kernel of the chain calls pdl_launch_dependents() first (the next
+// kernel's CTAs may become resident as this one's drain) and pdl_wait() before it touches anything a predecessor
+// wrote (blocks until the preceding grid has completed and its memory is visible).  Both are no-ops for a kernel
+// launched the ordinary way.  EVERY thread of a PDL-launched kernel must pass pdl_wait() before it exits, so that
+// "grid complete" keeps implying "all earlier grids complete" along the chain.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // api.cu: CCVSQ_NO_PDL=1 switches the launch attribute off (A/B runs)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // tensor-core screen: codes per accumulator tile, and the K-extension that carries the bias
 // (the BF16 codebook shadow is [ccvsq_codebook_rows(K), D + SCREEN_EXT])
 constexpr int SCREEN_BN = 96;

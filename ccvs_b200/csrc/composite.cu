@@ -67,6 +67,8 @@ extern "C" int ccvsq_quantize_forward(const ccvsq_forward_args* a, void* stream)
   //         [6] max ||e|| (when the side data is built here) | [16, 16+K) per-code counts
   int32_t* hdr = a->header;
   CCVSQ_CUDA(cudaMemsetAsync(hdr, 0, (size_t)(CCVSQ_HEADER_INTS + K) * sizeof(int32_t), st));
+  // (all memsets come first: the kernels below form one programmatic-dependent-launch chain)
+  if (a->resid && !a->indices_only) CCVSQ_CUDA(cudaMemsetAsync(a->resid, 0, (size_t)K * D * sizeof(float), st));
   int32_t* q_count = hdr + 0;
   int32_t* fb_count = hdr + 1;
   int32_t* ticket = hdr + 3;
@@ -117,8 +119,7 @@ extern "C" int ccvsq_quantize_forward(const ccvsq_forward_args* a, void* stream)
   s.fin.M = (double)L.P * L.C;
   s.fin.N = (double)L.N;
   s.fin.beta = a->beta;
-  if (a->resid) {   // per-code residual sums on the same pass (EMA codebook update)
-    CCVSQ_CUDA(cudaMemsetAsync(a->resid, 0, (size_t)K * D * sizeof(float), st));
+  if (a->resid) {   // per-code residual sums on the same pass (EMA codebook update; zeroed at the top of the call)
     s.resid = a->resid;
     s.sub = 1.f;
   }

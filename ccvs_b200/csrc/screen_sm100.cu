@@ -528,6 +528,11 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
   }
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  // everything above (barriers, tensor-memory allocation, descriptor prefetch) touched nothing a predecessor
+  // writes: under programmatic dependent launch it overlaps the tail of prepare_codebook.  From here on the
+  // codebook shadow, max ||e|| and the zeroed queue counter are read.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // =========================== TMA producer (every CTA: its half of each B tile) ===============
@@ -868,13 +873,15 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
   cfg.blockDim = dim3(SCREEN_THREADS);
   cfg.dynamicSmemBytes = lay.total;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const int n_tiles = (K + BN - 1) / BN;          // rows [K, n_tiles*BN) of the shadow are padding (bias -3e38)
   CCVSQ_REQUIRE(n_tiles * BN <= K_pad, CCVSQ_BAD_SHAPE, "screen: codebook shadow has %d rows, the sweep needs %d",
                 K_pad, n_tiles * BN);

@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
   int* red_k = reinterpret_cast<int*>(red_d + XR * 16);   // [XR][16]
   __shared__ int64_t row_id[XR];
 
+  pdl_launch_dependents();
+  pdl_wait();                                     // the fallback list / the codebook norms come from predecessors
   const int64_t total_rows = row_list ? min((int64_t)row_count[0], max_rows) : L.N;
   if (row_list && total_rows == 0) return;   // the usual case of the fallback launch: nothing was flagged (every CTA
                                              // sees the same count, so the ticket below is skipped consistently)
@@ -213,8 +215,8 @@ static int launch_exact(const float* z, const Lay& L, const float* E, const floa
     if (blocks > cap) blocks = cap;
   }
   if (blocks < 1) blocks = 1;
-  search_exact_kernel<<<dim3((unsigned)blocks, slices), XT, smem, st>>>(z, L, E, e_sq, K, rows, keys,
-                                                                      row_count, max_rows, idx);
+  CCVSQ_CUDA(launch_pdl(search_exact_kernel, dim3((unsigned)blocks, slices), dim3(XT), smem, st, z, L, E, e_sq, K, rows, keys,
+                        row_count, max_rows, idx));
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
 }

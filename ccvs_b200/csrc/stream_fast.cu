@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
   extern __shared__ float4 tile4[];                 // [FPT][CS/4], chunk index ^ (position/4)
   __shared__ float s_red[FNT / 32];
   __shared__ bool s_last;
+  pdl_launch_dependents();
+  if (!IS_ASSIGN(MODE)) pdl_wait();   // (assign: the latents are nobody's output — its loads start before the wait)
   const int tid = threadIdx.x;
   // assign walks the tiles from the end: it runs right after the search, which read the latents front to back, so
   // the tail of z is what the L2 still holds (126 MB) — those tiles are re-read on chip instead of from HBM
@@ -135,7 +137,6 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
         if (HAS_X) prefetch_l2(a.x + nbase + (int64_t)c * L.S);
         if (has_g) prefetch_l2(a.g + nbase + (int64_t)c * L.S);
       }
-      if (tid < (FPT * L.mult + 15) / 16) prefetch_l2(a.idx + nb * FPT * L.mult + tid * 16);
     }
   }
 #pragma unroll
@@ -166,6 +167,14 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
     }
   }
 
+  // ---- everything below depends on the codes, which the search kernels in front of an assign write
+  if (IS_ASSIGN(MODE)) pdl_wait();
+  if (tile_in_group) {                               // codes of the tile one wave ahead -> L2
+    const int64_t ahead = (int64_t)CCVSQ_PREFETCH_WAVES * kNumSMs * (MODE == MODE_BACKWARD ? 2 : 4);
+    const int64_t nb = IS_ASSIGN(MODE) ? (int64_t)bx - ahead : (int64_t)bx + ahead;
+    if (nb >= 0 && nb < (int64_t)gridDim.x && tid < (FPT * L.mult + 15) / 16)
+      prefetch_l2(a.idx + nb * FPT * L.mult + tid * 16);
+  }
   // ---- gather the codebook rows of this tile into shared memory: one warp per position (4 positions per warp),
   // lanes over the 16-byte chunks of the row (QS <= 64: at most two per lane).  The four codes of a warp are read
   // by four lanes in ONE load and broadcast, and the rows go global -> shared with cp.async: the whole 32 KiB gather
@@ -316,6 +325,8 @@ template <int MODE>
 __global__ void __launch_bounds__(FNT) rows4_kernel(const StreamArgs a, const int64_t N, const int D) {
   __shared__ float s_red[FNT / 32];
   __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int U = 4;
   const int Q = D >> 2;
   const int64_t total = N * Q;
@@ -419,6 +430,8 @@ template <int MODE>
 __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kernel(const StreamArgs a, const int64_t N, const int D) {
   __shared__ float s_red[FNT / 32];
   __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int RPW = 4;
   const int lane = threadIdx.x & 31;
   const int Q = D >> 2, QL = D >> 7;                        // chunks per row / per lane
@@ -532,9 +545,9 @@ static int launch_cm4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
   const size_t smem = (size_t)FPT * CS * sizeof(float);
   const dim3 grid((unsigned)cdiv(L.P, FPT), (unsigned)nslab);
   if (CS <= 128) {
-    cm4_kernel<MODE, 1><<<grid, FNT, smem, st>>>(a, L, CS);
+    CCVSQ_CUDA(launch_pdl(cm4_kernel<MODE, 1>, grid, dim3(FNT), smem, st, a, L, CS));
   } else {
-    cm4_kernel<MODE, 2><<<grid, FNT, smem, st>>>(a, L, CS);
+    CCVSQ_CUDA(launch_pdl(cm4_kernel<MODE, 2>, grid, dim3(FNT), smem, st, a, L, CS));
   }
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
@@ -545,14 +558,14 @@ static int launch_rows4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
   if (L.D % 128 == 0) {
     const int64_t blocks = (L.N + 4 * (FNT / 32) - 1) / (4 * (FNT / 32));
     CCVSQ_REQUIRE(blocks < (1ll << 31), CCVSQ_BAD_SHAPE, "stream kernel: %lld CTAs exceed the grid limit", (long long)blocks);
-    rowsw_kernel<MODE><<<(unsigned)blocks, FNT, 0, st>>>(a, L.N, L.D);
+    CCVSQ_CUDA(launch_pdl(rowsw_kernel<MODE>, dim3((unsigned)blocks), dim3(FNT), 0, st, a, L.N, L.D));
     CCVSQ_LAUNCH_CHECK();
     return CCVSQ_OK;
   }
   const int64_t total = L.N * (L.D >> 2);
   const int64_t blocks = (total + 4 * FNT - 1) / (4 * FNT);
   CCVSQ_REQUIRE(blocks < (1ll << 31), CCVSQ_BAD_SHAPE, "stream kernel: %lld CTAs exceed the grid limit", (long long)blocks);
-  rows4_kernel<MODE><<<(unsigned)blocks, FNT, 0, st>>>(a, L.N, L.D);
+  CCVSQ_CUDA(launch_pdl(rows4_kernel<MODE>, dim3((unsigned)blocks), dim3(FNT), 0, st, a, L.N, L.D));
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
 }

@@ -84,6 +84,8 @@ static inline size_t tile_smem_bytes(const Lay& L) { return (size_t)PT * (L.C + 
 __global__ void prepare_codebook_kernel(const float* __restrict__ E, int K, int K_pad, int D,
                                         float* __restrict__ e_sq, __nv_bfloat16* __restrict__ Eb,
                                         unsigned int* __restrict__ e_max_bits) {
+  pdl_launch_dependents();   // the screen may set itself up (barriers, tensor memory) while the shadow is built
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K_pad) return;
@@ -135,6 +137,8 @@ __global__ void __launch_bounds__(NT) rescore_queue_kernel(const float* __restri
                                                            int64_t* __restrict__ idx,
                                                            int64_t* __restrict__ fb_rows,
                                                            int32_t* __restrict__ fb_count, int64_t fb_cap) {
+  pdl_launch_dependents();
+  pdl_wait();                               // the queue is written by the screen kernel
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * NW;
   const int total = *q_count;
@@ -498,10 +502,9 @@ extern "C" int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, c
   CCVSQ_REQUIRE(L.D <= 512, CCVSQ_UNSUPPORTED, "rescore: D=%d > 512", L.D);
   int64_t blocks = (L.N + NW - 1) / NW;
   if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-  rescore_queue_kernel<<<(unsigned)blocks, NT, 0, (cudaStream_t)stream>>>(
-      z, L, E, e_sq, K, n_cand, queue_count, queue_rows, queue_cand, queue_flags, idx, fallback_ws,
-      fallback_count, fallback_capacity);
-  CCVSQ_LAUNCH_CHECK();
+  CCVSQ_CUDA(launch_pdl(rescore_queue_kernel, dim3((unsigned)blocks), dim3(NT), 0, (cudaStream_t)stream, z, L, E, e_sq, K,
+                        n_cand, queue_count, queue_rows, queue_cand, queue_flags, idx, fallback_ws, fallback_count,
+                        fallback_capacity));
   return CCVSQ_OK;
 }
 
