@@ -528,11 +528,13 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
   }
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  // everything above (barriers, tensor-memory allocation, descriptor prefetch) touched nothing a predecessor
-  // writes: under programmatic dependent launch it overlaps the tail of prepare_codebook.  From here on the
-  // codebook shadow, max ||e|| and the zeroed queue counter are read.
+  // Programmatic dependent launch: everything above (barriers, tensor-memory allocation, descriptor prefetch)
+  // touched nothing a predecessor writes, and neither do the latent loads of the A loaders / the L2 prefetcher —
+  // all of that overlaps the tail of prepare_codebook.  The roles that read the codebook shadow (TMA), max ||e||
+  // (epilogue) or consume them through barriers (MMA) wait first; the others wait before they exit, so that this
+  // grid's completion still implies the predecessor's.
   pdl_launch_dependents();
-  pdl_wait();
+  if (warp < 3 || (warp >= 4 && warp < 8)) pdl_wait();
 
   if (warp == 0) {
     // =========================== TMA producer (every CTA: its half of each B tile) ===============
@@ -634,6 +636,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         }
       }
     }
+    pdl_wait();
   } else if (warp >= 8) {
     // =========================== A loaders: FP32 global -> BF16 -> tensor memory ================
     const int q = warp & 3, h = (warp - 8) >> 2;
@@ -698,6 +701,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         if (CG == 1) mbar_arrive(a_full(ab)); else mbar_arrive_cluster(af_bar + 8u * ab);
       }
     }
+    pdl_wait();
   } else if (warp >= 4) {
     // =========================== epilogue: one latent row per thread, all codes =================
     const int q = warp & 3;
