@@ -120,12 +120,42 @@ def make_inputs(workload: str, device, seed: int):
     return z, cb, n
 
 
+_ORIGINAL_AFFINITY = None
+
+
+def bind_near_gpu(cuda_index: int):
+    """Pin this rank's host thread (and with it the pages of the pinned buffers it allocates) to the CPUs NVML
+    reports as local to its GPU: with 8 ranks each pulling ~55 GB/s over PCIe, host buffers on the far socket would
+    cross the inter-socket link.  Returns a short description for the JSON line; never fatal."""
+    global _ORIGINAL_AFFINITY
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = os.sched_getaffinity(0)
+        if not after:
+            os.sched_setaffinity(0, before)
+            return "unchanged (empty NVML affinity)"
+        _ORIGINAL_AFFINITY = before
+        return f"{len(after)} of {len(before)} CPUs (NVML affinity of the rank's GPU)"
+    except Exception as e:  # noqa: BLE001
+        return f"unchanged ({type(e).__name__})"
+
+
 def use_all_host_threads() -> int:
     """The CPU legs run on every host core this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers,
     which would silently time the reference on ONE thread: override it explicitly."""
     try:
+        if _ORIGINAL_AFFINITY:
+            os.sched_setaffinity(0, _ORIGINAL_AFFINITY)      # undo the GPU-local binding for the CPU legs
         n = len(os.sched_getaffinity(0))
-    except AttributeError:
+    except (AttributeError, OSError):
         n = os.cpu_count() or 1
     torch.set_num_threads(max(1, n))
     return torch.get_num_threads()
@@ -207,6 +237,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--search-mode", default="auto", choices=["auto", "tensor", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's local CPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -232,6 +263,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_affinity = "not requested" if args.no_numa_bind else bind_near_gpu(local_rank)
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -481,7 +513,8 @@ def main():
                    "layout": [clips, frames, D, h, w_], "distribution": "T (E~N(0,1), z=E[randint]+0.5N(0,1))",
                    "search_mode": args.search_mode, "screen_operands": "bf16 (fp32 accumulate), fp32 rescoring",
                    "l2": f"inputs larger than L2 ({z.numel() * 4 / 2**20:.0f} MiB of latents per step)",
-                   "parallelism": f"frame-sharded x{world}, codebook replicated, no data-path collective"},
+                   "parallelism": f"frame-sharded x{world}, codebook replicated, no data-path collective",
+                   "host_affinity": host_affinity},
         "e2e": e2e, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "kernel_breakdown": breakdown, "hbm_kernels": extra, "small_batch": small,
     }

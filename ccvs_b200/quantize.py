@@ -194,12 +194,25 @@ class VectorQuantizer(nn.Module):
             raise TypeError(f"the reference quantizer is FP32 end to end; got {z.dtype}")
         z = z.contiguous()
         w = self.embedding.weight
+        if z.numel() == 0:
+            return self._forward_empty(z, w)
         if self.normalize:
             z_q, loss, idx, perp = self._forward_normalized(z, w)
         else:
             z_q, loss, idx, perp, counts = _QuantizeFn.apply(z, w, self)
             self.last_counts = counts
         idx2 = idx.view(-1, 1)
+        return z_q, loss, (perp, LazyOneHot(idx2, self.n_e, z.dtype), idx2)
+
+    def _forward_empty(self, z, w):
+        """Empty batch, as the reference handles it (quantize.py:40-74 on zero rows): empty z_q and indices, and the
+        means over zero elements make loss and perplexity NaN; backward gives an empty dz and a zero dE."""
+        nan = float("nan")
+        z_q = z + torch.zeros_like(z)
+        loss = (z.sum() + w.sum() * 0.0) + nan            # value NaN; d/dz empty, d/dE exactly zero
+        perp = torch.full((), nan, dtype=torch.float32, device=z.device)
+        idx2 = torch.empty(0, 1, dtype=torch.int64, device=z.device)
+        self.last_counts = torch.zeros(self.n_e, dtype=torch.int32, device=z.device)
         return z_q, loss, (perp, LazyOneHot(idx2, self.n_e, z.dtype), idx2)
 
     def _forward_normalized(self, z, w):
@@ -227,6 +240,8 @@ class VectorQuantizer(nn.Module):
         z = z.contiguous()
         if z.dtype != torch.float32:
             raise TypeError(f"the reference quantizer is FP32 end to end; got {z.dtype}")
+        if z.numel() == 0:
+            return torch.empty(0, dtype=torch.int64, device=z.device)
         lay = ops.layout_of(z.shape, self.e_dim, self.mult)
         return ops.quantize_forward(z, lay, self.embedding.weight, self.beta, self.search_mode, self.n_cand,
                                     self.margin_tau, self.exact_fallback, cb=self._cb_cached(), indices_only=True).idx

@@ -588,3 +588,19 @@ def test_forward_with_fused_code_statistics(shape, K, D):
     idx = plain.idx.cpu()
     ref = torch.zeros(K, D, dtype=torch.float64).index_add_(0, idx, rows - cb.double()[idx])
     torch.testing.assert_close(fused.resid.cpu().double(), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_empty_batch_behaves_like_the_reference():
+    """Zero latents (an empty shard): the reference returns empty z_q / indices and NaN loss / perplexity (means over
+    zero elements), backward gives an empty dz and a zero dE; embed_code of no codes is an empty tensor."""
+    vq = VectorQuantizer(16, 8, 0.25).to(DEV)
+    z = torch.zeros(0, 8, 4, 4, device=DEV, requires_grad=True)
+    z_q, loss, (perp, enc, idx) = vq(z)
+    assert z_q.shape == z.shape and tuple(idx.shape) == (0, 1) and idx.dtype == torch.int64
+    assert tuple(enc.shape) == (0, 16)
+    assert torch.isnan(loss) and torch.isnan(perp)
+    (z_q.sum() + loss).backward()
+    assert z.grad.shape == z.shape
+    assert vq.embedding.weight.grad.shape == (16, 8) and float(vq.embedding.weight.grad.abs().sum()) == 0.0
+    assert vq.encode_indices(z.detach()).shape == (0,)
+    assert vq.embed_code(torch.zeros(0, 4, 4, dtype=torch.int64, device=DEV)).shape == (0, 4, 4, 8)

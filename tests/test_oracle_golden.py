@@ -133,3 +133,12 @@ def test_oracle_decoder_head_is_a_function_of_the_code():
     full = vq_oracle.decoder_head(code, cb, weight, bias, (h, w))                      # [G, C_out, h, w]
     per_code = vq_oracle.decoder_head(torch.arange(K).view(K, 1), cb, weight, bias, (1, 1)).view(K, C_out)
     torch.testing.assert_close(full.permute(0, 2, 3, 1).reshape(-1, C_out), per_code[code.view(-1)], rtol=1e-6, atol=1e-6)
+
+
+def test_oracle_empty_batch_matches_reference_behaviour():
+    """What the unmodified reference does on zero latents (checked by running quantize.py on CPU): empty z_q and
+    indices, NaN loss and perplexity.  The oracle restates it; the CUDA module is tested against the same facts."""
+    z, cb = torch.zeros(0, 8, 4, 4), torch.randn(16, 8)
+    r = vq_oracle.forward(z, cb, 0.25)
+    assert r.z_q.shape == z.shape and tuple(r.indices.shape) == (0, 1)
+    assert torch.isnan(r.loss) and torch.isnan(r.perplexity)
