@@ -159,8 +159,15 @@ struct StreamArgs {
   const float* pos;       // gather (row-major only): rows added to the gathered rows, out[n] = E[idx[n]] + pos[n % pos_period]
   int64_t pos_period;
   int K;
+  bool x_stable;          // assign only: x was complete before this launch chain began (the composite forward starts with
+                          // ordinary launches), so its loads may be issued before pdl_wait(); false = wait first
   FinArgs fin;
 };
+
+// ccvsq_screen for the composite forward (screen_sm100.cu): z is known to be complete before the chain starts
+int screen_launch_stable_z(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
+                           float margin_tau, int n_cand, int64_t* idx, int32_t* queue_count, int32_t* queue_rows,
+                           int32_t* queue_cand, uint8_t* queue_flags, void* stream);
 
 bool stream_fast_supported(const StreamArgs& a, const Lay& L);
 int stream_fast_launch(int mode, const StreamArgs& a, const Lay& L, cudaStream_t st);

@@ -94,8 +94,8 @@ extern "C" int ccvsq_quantize_forward(const ccvsq_forward_args* a, void* stream)
     int32_t* q_cand = (int32_t*)(ws + p.q_cand);
     uint8_t* q_flags = ws + p.q_flags;
     int64_t* fb_ws = (int64_t*)(ws + p.fb_ws);
-    if (int rc = ccvsq_screen(a->z, a->lay, e_bf16, e_max, K, a->margin_tau, a->n_cand, a->idx, q_count, q_rows, q_cand,
-                              q_flags, stream))
+    if (int rc = screen_launch_stable_z(a->z, a->lay, e_bf16, e_max, K, a->margin_tau, a->n_cand, a->idx, q_count, q_rows,
+                                        q_cand, q_flags, stream))
       return rc;
     if (a->ev_search_end) CCVSQ_CUDA(cudaEventRecord((cudaEvent_t)a->ev_search_end, st));
     const bool fb = a->exact_fallback != 0;
@@ -113,6 +113,7 @@ extern "C" int ccvsq_quantize_forward(const ccvsq_forward_args* a, void* stream)
   if (a->indices_only) return CCVSQ_OK;
   StreamArgs s = {};
   s.x = a->z; s.E = a->E; s.idx = a->idx; s.out = a->zq; s.sq_err = sq_err; s.counts = counts; s.K = K;
+  s.x_stable = true;      // z was complete before prepare_codebook (an ordinary launch) started
   s.fin.ticket = ticket;
   s.fin.loss = a->loss;
   s.fin.perplexity = a->perplexity;

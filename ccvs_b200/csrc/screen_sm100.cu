@@ -356,6 +356,8 @@ struct ScreenOut {
   int32_t* q_rows;         // [N]
   int32_t* q_cand;         // [N, n_cand]
   uint8_t* q_flags;        // [N]
+  bool z_stable;           // z was complete before this launch chain began (set by the composite forward, whose first
+                           // operations are ordinary launches): the latent loads may start before pdl_wait()
   // diagnostics (all may be null)
   int32_t* dbg_cand;       // [N, n_cand]
   float* dbg_score;        // [N, n_cand]
@@ -534,7 +536,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
   // (epilogue) or consume them through barriers (MMA) wait first; the others wait before they exit, so that this
   // grid's completion still implies the predecessor's.
   pdl_launch_dependents();
-  if (warp < 3 || (warp >= 4 && warp < 8)) pdl_wait();
+  if (!out.z_stable || warp < 3 || (warp >= 4 && warp < 8)) pdl_wait();
 
   if (warp == 0) {
     // =========================== TMA producer (every CTA: its half of each B tile) ===============
@@ -966,6 +968,24 @@ extern "C" int ccvsq_screen(const float* z, ccvsq_layout lay, const void* E_bf16
   out.q_flags = queue_flags;
   return screen_impl(z, lay, E_bf16, e_max, K, margin_tau, n_cand, out, 2, stream);
 }
+
+// internal (composite.cu): same as ccvsq_screen, with the promise that z is not written by the kernel right in front
+namespace ccvsq {
+int screen_launch_stable_z(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
+                           float margin_tau, int n_cand, int64_t* idx, int32_t* queue_count, int32_t* queue_rows,
+                           int32_t* queue_cand, uint8_t* queue_flags, void* stream) {
+  CCVSQ_REQUIRE(idx && queue_count && queue_rows && queue_cand && queue_flags, CCVSQ_NULL_POINTER,
+                "screen: null output pointer");
+  ScreenOut out = {};
+  out.idx = idx;
+  out.q_count = queue_count;
+  out.q_rows = queue_rows;
+  out.q_cand = queue_cand;
+  out.q_flags = queue_flags;
+  out.z_stable = true;
+  return screen_impl(z, lay, E_bf16, e_max, K, margin_tau, n_cand, out, 2, stream);
+}
+}  // namespace ccvsq
 
 extern "C" int ccvsq_screen_trace(const float* z, ccvsq_layout lay, const void* E_bf16, const float* e_max, int K,
                                   float margin_tau, int n_cand, int64_t* idx, int32_t* queue_count,

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
   __shared__ float s_red[FNT / 32];
   __shared__ bool s_last;
   pdl_launch_dependents();
-  if (!IS_ASSIGN(MODE)) pdl_wait();   // (assign: the latents are nobody's output — its loads start before the wait)
+  const bool late_wait = IS_ASSIGN(MODE) && a.x_stable;   // the latents were complete before the chain began: their
+  if (!late_wait) pdl_wait();                            // loads may start before the wait (the codes may not)
   const int tid = threadIdx.x;
   // assign walks the tiles from the end: it runs right after the search, which read the latents front to back, so
   // the tail of z is what the L2 still holds (126 MB) — those tiles are re-read on chip instead of from HBM
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 2 : CCVSQ_CM4_MIN
   }
 
   // ---- everything below depends on the codes, which the search kernels in front of an assign write
-  if (IS_ASSIGN(MODE)) pdl_wait();
+  if (late_wait) pdl_wait();
   if (tile_in_group) {                               // codes of the tile one wave ahead -> L2
     const int64_t ahead = (int64_t)CCVSQ_PREFETCH_WAVES * kNumSMs * (MODE == MODE_BACKWARD ? 2 : 4);
     const int64_t nb = IS_ASSIGN(MODE) ? (int64_t)bx - ahead : (int64_t)bx + ahead;

@@ -13,6 +13,9 @@
  *     allocates, frees or retains device memory;
  *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*); no call
  *     synchronises the device;
+ *   - calls on one stream keep stream order.  Internally consecutive kernels of this library are chained with
+ *     programmatic dependent launch (a kernel's prologue may overlap its predecessor's tail; it waits for the
+ *     predecessor before reading any argument buffer) — invisible to the caller, no extra synchronisation needed;
  *   - return 0 on success, a negative ccvsq_status otherwise; ccvsq_last_error() gives text;
  *   - no exceptions cross the ABI, no torch types in any signature.
  *
