@@ -98,6 +98,40 @@ class _QuantizeFn(torch.autograd.Function):
         return dz, dE, None
 
 
+class _AssignFn(torch.autograd.Function):
+    """Assign with GIVEN indices against a given table: z_q = fl(z + fl(T[idx] - z)), loss, perplexity, counts, and
+    the same backward as _QuantizeFn (dz, dT).  Used by the `normalize=True` variant with mult == 1, where the
+    search runs on the raw codebook (quantize.py:45-50) but everything after it sees the L2-normalised rows
+    (quantize.py:56-64): T = E / ||E|| is K rows of torch ops, all N-sized work stays in the kernels."""
+
+    @staticmethod
+    def forward(ctx, z, table, idx, beta):
+        lay = ops.layout_of(z.shape, table.shape[1], 1)
+        K, D = table.shape
+        zq, sq, counts = ops.assign(z, lay, table.detach(), idx)
+        _, loss, perp = ops.finalize(K, D, float(z.numel()), float(lay.rows), beta, counts=counts, sq_err=sq,
+                                     want_loss=True, want_perplexity=True)
+        ctx.lay = lay
+        ctx.beta = beta
+        ctx.save_for_backward(z, table, idx)
+        ctx.mark_non_differentiable(perp, counts)
+        return zq, loss, perp, counts
+
+    @staticmethod
+    def backward(ctx, g_zq, g_loss, _gp, _gc):
+        z, table, idx = ctx.saved_tensors
+        dev = z.device
+        if g_loss is None:
+            g_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        g_loss = g_loss.to(torch.float32).contiguous()
+        want_dz, want_dT = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (want_dz or want_dT):
+            return None, None, None, None
+        g = None if (g_zq is None or not want_dz) else g_zq.to(torch.float32).contiguous()
+        dz, dT = ops.quantize_backward(z, ctx.lay, table.detach(), idx, g, g_loss, ctx.beta, want_dz, want_dT)
+        return dz, dT, None, None
+
+
 class _GatherFn(torch.autograd.Function):
     """E[idx] written in z's layout, with the embedding backward as a per-code scatter-add.
     Used by the `normalize=True` variant, whose remaining elementwise graph (quantize.py:56-64)
@@ -216,11 +250,20 @@ class VectorQuantizer(nn.Module):
         return z_q, loss, (perp, LazyOneHot(idx2, self.n_e, z.dtype), idx2)
 
     def _forward_normalized(self, z, w):
-        # search + gather in our kernels; the normalisation and its chain rule stay in autograd
         lay = ops.layout_of(z.shape, self.e_dim, self.mult)
         cb = self._prepared()
         with torch.no_grad():
             idx = ops.search(z.detach(), lay, cb, self.search_mode, self.n_cand, self.margin_tau, self.exact_fallback)
+        if self.mult == 1:
+            # a position carries ONE code, so its normalised vector is a function of the code: normalise the K rows
+            # (autograd-tracked torch ops on [K, D]) and run assign / backward on that table
+            table = (w / torch.norm(w, p=2, dim=1, keepdim=True)).contiguous()           # quantize.py:56-57
+            zq, loss, perp, counts = _AssignFn.apply(z, table, idx, self.beta)
+            self.last_counts = counts
+            return zq, loss, idx, perp
+        # mult > 1: the norm runs over the concatenation of several codes; gather in our kernel, the normalisation
+        # and its chain rule stay in autograd
+        with torch.no_grad():
             counts = torch.bincount(idx, minlength=self.n_e).to(torch.int32)
             _, _, perp = ops.finalize(self.n_e, self.e_dim, float(z.numel()), float(lay.rows), self.beta, counts=counts,
                                       want_perplexity=True)
