@@ -32,6 +32,7 @@
 //   warps 8-15  A loaders: global FP32 -> BF16 -> tcgen05.st, row norms for the margin
 #include <cuda.h>
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -216,6 +217,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 columns into the low half of a 32-register chunk; the high half is set to -inf so the 32-column max tree /
+// candidate logic can be reused unchanged (an 80-column accumulator is 32 + 32 + 16)
+__device__ __forceinline__ void tmem_ld16_pad(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 16; i < 32; ++i) r[i] = 0xFF800000u;
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -270,11 +284,11 @@ constexpr uint32_t CO_STRIDE = ENT_STRIDE;
 constexpr uint32_t CO_OFFSET = BM * 16;
 constexpr uint32_t LIST_BYTES = LCAP * ENT_STRIDE;
 constexpr int SCREEN_THREADS = 512;
-constexpr int MAX_SLOTS = 8;
+constexpr int MAX_SLOTS = 16;
 // tensor-memory columns (32-bit): two accumulators, the constant bias-extension A block, A buffers
 //   [0, nacc*BN) accumulators | [nacc*BN, +8) bias-extension A block | then abuf_n A buffers of D/2
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int MAX_ACC = 4;
+constexpr int MAX_ACC = 8;
 
 struct ScreenSmem {
   uint32_t slots, list, norm, drop, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
@@ -786,11 +800,13 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr0, ra);
         tmem_ld_wait();
-        tmem_ld32(taddr0 + 32, rb);
-        process(ra, 0);
-        tmem_ld_wait();
-        if constexpr (BN == 96) {
-          tmem_ld32(taddr0 + 64, ra);
+        if constexpr (BN >= 64) {
+          tmem_ld32(taddr0 + 32, rb);
+          process(ra, 0);
+          tmem_ld_wait();
+        }
+        if constexpr (BN == 96 || BN == 80) {
+          if constexpr (BN == 96) tmem_ld32(taddr0 + 64, ra); else tmem_ld16_pad(taddr0 + 64, ra);
           process(rb, 32);
           tmem_ld_wait();
         }
@@ -799,7 +815,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         if (lane == 0) {
           if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
         }
-        if constexpr (BN == 96) process(ra, 64); else process(rb, 32);
+        if constexpr (BN == 96 || BN == 80) process(ra, 64); else if constexpr (BN == 64) process(rb, 32); else process(ra, 0);
         if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
       }
 
@@ -857,7 +873,7 @@ template <int CG, int BN>
 static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const float* e_max,
                          float margin_scale, int K, int K_pad, int D, int n_cand, int nacc, int abuf,
                          const ScreenOut& out, cudaStream_t st) {
-  static_assert(BN == 96 || BN == 64, "epilogue is written for 2 or 3 chunks of 32 columns");
+  static_assert(BN == 96 || BN == 80 || BN == 64 || BN == 32, "epilogue is written for 1, 2, 2.5 or 3 chunks of 32 columns");
   const int dblk = D / 64;
   const ScreenSmem lay = screen_smem_layout(dblk, CG, BN);
   CCVSQ_REQUIRE(lay.nslots >= 1, CCVSQ_UNSUPPORTED, "screen: D=%d leaves room for %d B slots", D, lay.nslots);
@@ -906,6 +922,16 @@ static ScreenPlan plan_screen(int K, int D) {
   const int a_cols = D / 2;
   auto fits = [&](int bn, int nacc, int abuf) { return nacc * bn + 8 + abuf * a_cols <= (int)TMEM_COLS; };
   static const int forced_bn = [] { const char* e = getenv("CCVSQ_SCREEN_BN"); return e ? atoi(e) : 0; }();
+  // CCVSQ_SCREEN_PLAN=bn,nacc,abuf forces a plan for short sweeps (A/B runs)
+  static const ScreenPlan forced = [] {
+    ScreenPlan p = {0, 0, 0};
+    const char* e = getenv("CCVSQ_SCREEN_PLAN");
+    if (e) sscanf(e, "%d,%d,%d", &p.bn, &p.nacc, &p.abuf);
+    return p;
+  }();
+  if (forced.bn && (K + 95) / 96 < 24 && (forced.bn == 64 || forced.bn == 96) && forced.nacc >= 1 && forced.nacc <= MAX_ACC &&
+      forced.abuf >= 1 && forced.abuf <= 2 && fits(forced.bn, forced.nacc, forced.abuf))
+    return forced;
   const bool long_sweep = (K + 95) / 96 >= 24;
   ScreenPlan best = {96, 2, 1};
   const ScreenPlan order_long[] = {{96, 3, 2}, {96, 3, 1}, {64, 3, 2}, {64, 3, 1}, {96, 2, 2}, {96, 2, 1}};
