@@ -479,6 +479,15 @@ __device__ __forceinline__ void load_chunk(float (&v)[32], const float* __restri
   }
 }
 
+// per-tile stamps of ONE sweep (the fourth) for the DBG kernel: trace[cta][16 + tile][slot]
+#define CCVSQ_TILE_STAMP(TL, J, SLOT)                                                                              \
+  do {                                                                                                             \
+    if constexpr (DBG) {                                                                                           \
+      if (out.trace && (TL) == 3 && (J) < 16 && lane == 0)                                                         \
+        out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + 16 + (J)) * 8 + (SLOT)] = clock64();                        \
+    }                                                                                                              \
+  } while (0)
+
 template <int CG, bool DBG, int BN>
 __global__ void __launch_bounds__(SCREEN_THREADS, 1)
 screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_ext,
@@ -559,9 +568,11 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     int slot = 0;
     uint32_t phase = 0;
     const uint32_t fb0 = (CG == 1) ? full_bar(0) : mapa(full_bar(0), 0);
-    for (int gt = group; gt < num_group_tiles; gt += num_groups) {
+    uint32_t tl = 0;
+    for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(empty_bar(slot), phase ^ 1);
+        CCVSQ_TILE_STAMP(tl, j, 6);
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(full_bar(slot), lay.slot_tx * CG);
           const uint32_t fb = fb0 + 8u * slot;
@@ -573,6 +584,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           tma_load_2d<CG>(dst + lay.ext_off + ROWS * 16, &map_ext, fb, dblk * 64 + 8, row0);
         }
         __syncwarp();
+        CCVSQ_TILE_STAMP(tl, j, 7);
         if (++slot == nslots) { slot = 0; phase ^= 1; }
       }
     }
@@ -588,11 +600,13 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         for (int j = 0; j < n_tiles; ++j) {
           if (j == 0) { if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 0] = clock64(); } }
           mbar_wait(tmem_empty(b), b_phase ^ 1);
+          CCVSQ_TILE_STAMP(tl, j, 0);
           if (j == 0) {
             mbar_wait(a_full(ab), a_phase);
             if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 1] = clock64(); }
           }
           mbar_wait(full_bar(slot), phase);
+          CCVSQ_TILE_STAMP(tl, j, 1);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d_tmem = tmem_base + b * BN;
@@ -613,6 +627,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
             if (j == n_tiles - 1) umma_commit<CG>(a_empty(ab));   // last reader of this A buffer
           }
           __syncwarp();
+          CCVSQ_TILE_STAMP(tl, j, 2);
           if (j == n_tiles - 1) { if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 2] = clock64(); } }
           if (++slot == nslots) { slot = 0; phase ^= 1; }
           if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
@@ -743,6 +758,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
 
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(tmem_full(b), b_phase);
+        if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 3);
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
         const int col0 = j * BN;
@@ -815,7 +831,9 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         if (lane == 0) {
           if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
         }
+        if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 4);
         if constexpr (BN == 96 || BN == 80) process(ra, 64); else if constexpr (BN == 64) process(rb, 32); else process(ra, 0);
+        if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 5);
         if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
       }
 
@@ -992,7 +1010,9 @@ extern "C" int ccvsq_screen(const float* z, ccvsq_layout lay, const void* E_bf16
   out.q_rows = queue_rows;
   out.q_cand = queue_cand;
   out.q_flags = queue_flags;
-  return screen_impl(z, lay, E_bf16, e_max, K, margin_tau, n_cand, out, 2, stream);
+  // CCVSQ_SCREEN_CG=1: single-CTA MMA (M = 128 per CTA, no pairing) instead of the 2-CTA form, for A/B runs
+  static const int cg = [] { const char* e = getenv("CCVSQ_SCREEN_CG"); return (e && atoi(e) == 1) ? 1 : 2; }();
+  return screen_impl(z, lay, E_bf16, e_max, K, margin_tau, n_cand, out, cg, stream);
 }
 
 // internal (composite.cu): same as ccvsq_screen, with the promise that z is not written by the kernel right in front

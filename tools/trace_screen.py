@@ -39,3 +39,16 @@ print(f"loaders, sweeps 2-12: wait for free buffer {(ld[:, 2:13, 4] - ld[:, 2:13
 ep = tr.double()
 oke = (ep[:, 1:13, 6] > 0) & (ep[:, 1:13, 7] > 0)
 print(f"epilogue, sweeps 1-12: sweep {(ep[:, 1:13, 7] - ep[:, 1:13, 6])[oke].mean():.0f} cyc; gap to next sweep start {(ep[:, 2:13, 6] - ep[:, 1:12, 7])[oke[:, 1:] & oke[:, :-1]].mean():.0f} cyc")
+
+# per-tile stamps of the fourth sweep (trace[cta][16 + tile][slot]); leader CTA 0 and its peer CTA 1
+tn = ["mma:acc free", "mma:B landed", "mma:issued", "ep:acc full", "ep:released", "ep:tile done", "tma:slot free", "tma:issued"]
+for cta in (0, 1):
+    t = tr[cta][16:32]
+    vals = t[t > 0]
+    if vals.numel() == 0:
+        continue
+    t0 = int(vals.min())
+    print(f"--- CTA {cta}, sweep 3, per tile (cycles since the first stamp of the sweep)")
+    for j in range(16):
+        row = [int(v) - t0 if int(v) else -1 for v in t[j]]
+        print(f"tile {j:2d}: " + "  ".join(f"{nm}={v:6d}" for nm, v in zip(tn, row)))
