@@ -224,7 +224,12 @@ class VectorQuantizer(nn.Module):
         exactly as quantize.py:32-74."""
         if not z.is_cuda:
             raise RuntimeError("ccvs_b200.VectorQuantizer runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if z.dtype != torch.float32:
+        in_dtype = z.dtype
+        if in_dtype in (torch.float16, torch.bfloat16):
+            # mixed-precision callers (the reference trains under apex amp, tools/engine.py:11-14): the latents are
+            # upcast, the whole path runs in FP32 as specified, and z_q goes back in the caller's dtype
+            z = z.float()
+        elif in_dtype != torch.float32:
             raise TypeError(f"the reference quantizer is FP32 end to end; got {z.dtype}")
         z = z.contiguous()
         w = self.embedding.weight
@@ -235,8 +240,10 @@ class VectorQuantizer(nn.Module):
         else:
             z_q, loss, idx, perp, counts = _QuantizeFn.apply(z, w, self)
             self.last_counts = counts
+        if in_dtype != torch.float32:
+            z_q = z_q.to(in_dtype)
         idx2 = idx.view(-1, 1)
-        return z_q, loss, (perp, LazyOneHot(idx2, self.n_e, z.dtype), idx2)
+        return z_q, loss, (perp, LazyOneHot(idx2, self.n_e, in_dtype), idx2)
 
     def _forward_empty(self, z, w):
         """Empty batch, as the reference handles it (quantize.py:40-74 on zero rows): empty z_q and indices, and the

@@ -604,3 +604,23 @@ def test_empty_batch_behaves_like_the_reference():
     assert vq.embedding.weight.grad.shape == (16, 8) and float(vq.embedding.weight.grad.abs().sum()) == 0.0
     assert vq.encode_indices(z.detach()).shape == (0,)
     assert vq.embed_code(torch.zeros(0, 4, 4, dtype=torch.int64, device=DEV)).shape == (0, 4, 4, 8)
+
+
+def test_half_precision_latents_are_upcast():
+    """Mixed-precision callers: FP16 / BF16 latents are upcast, the path runs in FP32 (indices equal those of the
+    FP32 call on the upcast values), z_q comes back in the caller's dtype and gradients flow through the cast."""
+    z, cb = vq_oracle.synth((4, 256, 16, 16), 1024, 256, "T", seed=77)
+    vq = VectorQuantizer(1024, 256, 0.25).to(DEV)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+    for dt in (torch.float16, torch.bfloat16):
+        zh = z.to(DEV).to(dt).requires_grad_(True)
+        z_q, loss, (_, _, idx) = vq(zh)
+        assert z_q.dtype == dt and z_q.shape == zh.shape and loss.dtype == torch.float32
+        with torch.no_grad():
+            ref_q, ref_loss, (_, _, ref_idx) = vq(zh.detach().float())
+        assert torch.equal(idx, ref_idx)
+        assert torch.equal(z_q.detach(), ref_q.to(dt))
+        torch.testing.assert_close(loss.detach(), ref_loss, rtol=1e-6, atol=0)
+        (z_q.float().sum() + loss).backward()
+        assert zh.grad is not None and zh.grad.dtype == dt
