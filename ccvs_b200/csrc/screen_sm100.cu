@@ -217,19 +217,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-// 16 columns into the low half of a 32-register chunk; the high half is set to -inf so the 32-column max tree /
-// candidate logic can be reused unchanged (an 80-column accumulator is 32 + 32 + 16)
-__device__ __forceinline__ void tmem_ld16_pad(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 16; i < 32; ++i) r[i] = 0xFF800000u;
-}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -816,13 +803,11 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr0, ra);
         tmem_ld_wait();
-        if constexpr (BN >= 64) {
-          tmem_ld32(taddr0 + 32, rb);
-          process(ra, 0);
-          tmem_ld_wait();
-        }
-        if constexpr (BN == 96 || BN == 80) {
-          if constexpr (BN == 96) tmem_ld32(taddr0 + 64, ra); else tmem_ld16_pad(taddr0 + 64, ra);
+        tmem_ld32(taddr0 + 32, rb);
+        process(ra, 0);
+        tmem_ld_wait();
+        if constexpr (BN == 96) {
+          tmem_ld32(taddr0 + 64, ra);
           process(rb, 32);
           tmem_ld_wait();
         }
@@ -832,7 +817,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
         }
         if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 4);
-        if constexpr (BN == 96 || BN == 80) process(ra, 64); else if constexpr (BN == 64) process(rb, 32); else process(ra, 0);
+        if constexpr (BN == 96) process(ra, 64); else process(rb, 32);
         if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 5);
         if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
       }
@@ -891,7 +876,7 @@ template <int CG, int BN>
 static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const float* e_max,
                          float margin_scale, int K, int K_pad, int D, int n_cand, int nacc, int abuf,
                          const ScreenOut& out, cudaStream_t st) {
-  static_assert(BN == 96 || BN == 80 || BN == 64 || BN == 32, "epilogue is written for 1, 2, 2.5 or 3 chunks of 32 columns");
+  static_assert(BN == 96 || BN == 64, "epilogue is written for 2 or 3 chunks of 32 columns (narrower / odd widths were measured and dropped: profiles/r01_screen_history.md)");
   const int dblk = D / 64;
   const ScreenSmem lay = screen_smem_layout(dblk, CG, BN);
   CCVSQ_REQUIRE(lay.nslots >= 1, CCVSQ_UNSUPPORTED, "screen: D=%d leaves room for %d B slots", D, lay.nslots);
