@@ -624,3 +624,18 @@ def test_half_precision_latents_are_upcast():
         torch.testing.assert_close(loss.detach(), ref_loss, rtol=1e-6, atol=0)
         (z_q.float().sum() + loss).backward()
         assert zh.grad is not None and zh.grad.dtype == dt
+
+
+def test_smoke_without_programmatic_dependent_launch():
+    """The kernels call griddepcontrol.wait / launch_dependents unconditionally; CCVSQ_NO_PDL=1 drops the launch
+    attribute (ordinary stream serialisation).  Same results either way: run the smoke check in a child process."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+    env = dict(os.environ, CCVSQ_NO_PDL="1")
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "smoke ok" in r.stdout

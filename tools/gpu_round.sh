@@ -21,5 +21,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:scre
 timeout 600 ncu --set full --clock-control none -k regex:"cm4_kernel|rows4_kernel|rowsw_kernel" -s 6 -c 6 -o $OUT/stream_c2 -f \
     python tools/ncu_stream.py c2 > $OUT/ncu_stream_c2.log 2>&1; echo "ncu stream c2 rc=$?"
 python tools/trace_screen.py c2 > $OUT/trace_c2.txt 2>&1
+[ -x tools/bin/tmem_bench ] && timeout 90 tools/bin/tmem_bench > $OUT/tmem_mma_microbench.txt 2>&1
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?"
 python tools/diag_forward.py c2 > $OUT/diag_c2.txt 2>&1
 python tools/show_bench.py $OUT/bench_c2.json $OUT/bench_c4.json $OUT/bench_c3.json $OUT/bench_c3d512.json $OUT/bench_c1.json $OUT/bench_train.json 2>&1 | tail -60
