@@ -13,7 +13,7 @@ losses); the perplexity comes from the summed per-code counts (quantize.py:67-68
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 
