@@ -120,6 +120,194 @@ def make_inputs(workload: str, device, seed: int):
     return z, cb, n
 
 
+def make_inputs_I(workload: str, device, seed: int):
+    """Distribution I (stress): E ~ U(-1/K, 1/K) exactly as quantize.py:30, z ~ N(0,1)."""
+    (clips, frames), D, h, w, K, _ = WORKLOADS[workload]
+    g = torch.Generator(device=device).manual_seed(seed)
+    cb = (torch.rand(K, D, generator=g, device=device) * 2 - 1) / K
+    z = torch.randn(clips, frames, D, h, w, generator=g, device=device)
+    return z, cb, clips * frames * h * w
+
+
+def rows_on_cpu(z):
+    """[clips, frames, C, h, w] on the device -> [N, C] rows in the reference's flatten order (quantize.py:40-42)."""
+    clips, frames, D, h, w = z.shape
+    return z.view(clips * frames, D, h * w).transpose(1, 2).reshape(-1, D).cpu()
+
+
+def index_match_record(dev, search_mode: str):
+    """Index agreement of the product path with the CPU oracle (SURVEY 8d / BASELINE metric "index match %"):
+    2^20 rows of the c2 geometry (four seeded batches) and 2^16 rows at K = 16384 (c3 geometry), distributions T and I.
+    The oracle's own FP32 distances classify every differing row: documented near-tie (gap <= 1e-6 relative) or
+    mismatch.  The oracle is the checker here, never the thing measured."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vq_oracle
+    from ccvs_b200 import VectorQuantizer
+    use_all_host_threads()
+    out = {}
+    t_start = time.perf_counter()
+    plans = {"c2": 4, "c3": 1}          # batches: 4 x 262144 = 2^20 rows ; c3 is cut to 2^16 rows below
+    for wl, batches in plans.items():
+        (clips, frames), D, h, w, K, _ = WORKLOADS[wl]
+        for dist in ("T", "I"):
+            tot = {"rows": 0, "exact": 0, "near_ties": 0, "mismatches": 0, "worst_rel_gap": 0.0}
+            for b in range(batches):
+                z, cb, n = (make_inputs if dist == "T" else make_inputs_I)(wl, dev, 9000 + 17 * b)
+                if wl == "c3":
+                    z = z[: (1 << 16) // (frames * h * w)].contiguous()
+                vq = VectorQuantizer(K, D, 0.25, search_mode=search_mode).to(dev).eval()
+                with torch.no_grad():
+                    vq.embedding.weight.copy_(cb)
+                idx = vq.encode_indices(z).cpu()
+                par = vq_oracle.classify_indices(idx, rows_on_cpu(z), cb.cpu())
+                tot["rows"] += par.n
+                tot["exact"] += par.exact
+                tot["near_ties"] += par.near_tie
+                tot["mismatches"] += par.mismatch
+                tot["worst_rel_gap"] = max(tot["worst_rel_gap"], par.worst_rel_gap)
+                del z, cb, vq, idx
+            tot["raw_pct"] = 100.0 * tot["exact"] / tot["rows"]
+            tot["excl_near_ties_pct"] = 100.0 * (tot["exact"] + tot["near_ties"]) / tot["rows"]
+            out[f"{'c2' if wl == 'c2' else 'k16384'}_{dist}"] = dict(tot, K=K, D=D)
+    out["oracle"] = ("oracle/vq_oracle.py (torch-CPU FP32 restatement of quantize.py:45-50, row-chunked); near tie = oracle "
+                     "distance gap <= 1e-6 relative; T = trained-like, I = fresh-init codebook (4-61 % near ties by construction)")
+    out["cpu_seconds"] = time.perf_counter() - t_start
+    return out
+
+
+def k16384_records(dev, search_mode: str, peaks_):
+    """The north_star's GEMM target: the screen kernel on the c4 shard (2^21 latents, K = 16384, D = 256), event-timed
+    per launch inside the composite call, with clocks sampled while it runs; plus the HBM-bound kernels on the
+    reference's real 8x8 layouts (c4, c3d512): per-launch medians."""
+    from ccvs_b200 import ops
+    bf16_peak, bf16_sust, hbm_peak, peak_src = peaks_
+    rec, hbm = None, {}
+    for wl in ("c4", "c3d512"):
+        (clips, frames), D, h, w, K, desc = WORKLOADS[wl]
+        z, cb, n = make_inputs(wl, dev, 1234)
+        lay = ops.layout_of(z.shape, D, 1)
+        pcb = ops.prepare_codebook(cb)
+        for _ in range(2):
+            o = ops.quantize_forward(z, lay, cb, 0.25, mode=search_mode, cb=pcb, indices_only=True)
+        torch.cuda.synchronize()
+        if wl == "c4":
+            sampler = ClockSampler(dev.index or 0)
+            sampler.start()
+            ops.PROFILER.reset(timing={"ccvsq_screen"})
+            reps = 50
+            for _ in range(reps):
+                o = ops.quantize_forward(z, lay, cb, 0.25, mode=search_mode, cb=pcb, indices_only=True)
+            torch.cuda.synchronize()
+            clocks = sampler.stop()
+            calls, tms = ops.PROFILER.summary().get("ccvsq_screen", (0, 0.0))
+            ops.PROFILER.reset(timing=False)
+            if calls:
+                flops = 2.0 * n * K * D
+                ach = flops / (tms / calls * 1e-3) / 1e12
+                rec = {"kernel": "screen_kernel", "workload": "c4 shard: 2^21 latents, K=16384, D=256 (BASELINE configs[3] per GPU)",
+                       "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                       "frac_of_sustained": ach / bf16_sust, "peak_source": f"{peak_src} (burst)", "launches": calls,
+                       "ms_per_launch": tms / calls, "algorithmic_flops_per_launch": flops, "clocks": clocks,
+                       "latents_per_sec_search_only": n / (tms / calls * 1e-3)}
+        idx = o.idx
+
+        def med(fn, reps=15):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                ts.append((a, b))
+            torch.cuda.synchronize()
+            v = sorted(x.elapsed_time(y) for x, y in ts)
+            return v[len(v) // 2]
+
+        zq = torch.empty_like(z)
+        hdr = torch.zeros(K + 4, dtype=torch.int32, device=dev)
+        sq = torch.zeros(1, dtype=torch.float64, device=dev)
+        dec = torch.empty(n, D, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        rl = ops.rows_layout(n, D)
+        t_assign = med(lambda: ops._call("ccvsq_assign", ops._ptr(z), lay, ops._ptr(cb), K, ops._ptr(idx), ops._ptr(zq), ops._ptr(sq),
+                                         ops._ptr(hdr), ops._stream(dev)))
+        t_rows = med(lambda: ops._call("ccvsq_gather", ops._ptr(idx), ops._ptr(cb), K, rl, ops._ptr(dec), ops._ptr(err), ops._stream(dev)))
+        t_cm = med(lambda: ops._call("ccvsq_gather", ops._ptr(idx), ops._ptr(cb), K, lay, ops._ptr(dec), ops._ptr(err), ops._stream(dev)))
+        gb = lambda bytes_, ms: bytes_ / (ms * 1e-3) / 1e9
+        hbm[wl] = {
+            "layout": [clips, frames, D, h, w], "K": K,
+            "assign": {"GBs": gb(n * (8 * D + 8), t_assign), "frac_of_hbm_peak": gb(n * (8 * D + 8), t_assign) / hbm_peak, "ms": t_assign},
+            "decode_gather": {"GBs": gb(n * (4 * D + 8), t_rows), "frac_of_hbm_peak": gb(n * (4 * D + 8), t_rows) / hbm_peak, "ms": t_rows},
+            "decode_gather_channel_major": {"GBs": gb(n * (4 * D + 8), t_cm), "frac_of_hbm_peak": gb(n * (4 * D + 8), t_cm) / hbm_peak, "ms": t_cm},
+        }
+        del z, cb, pcb, o, idx, zq, dec
+        torch.cuda.empty_cache()
+    hbm["note"] = "per-launch medians (CUDA events around one launch, 15 launches back to back); bytes = SURVEY 8d algorithmic bytes"
+    return rec, hbm
+
+
+def train_record(args, dev, world, cb, z, barrier):
+    """Training-mode quantizer (BASELINE configs[4]) at the c2 shape on every rank: forward + straight-through backward
+    + commitment loss + EMA codebook update with ONE NCCL all-reduce of the packed code statistics per step.  Three
+    variants, same steps: all-reduce overlapped with the backward (the product default), all-reduce serial in
+    front of the backward, and no all-reduce at all (sync off) -> how much of the collective is exposed."""
+    import torch.distributed as dist
+    from ccvs_b200.quantize import EMAVectorQuantizer
+    K, D = cb.shape
+    n_lat = z.numel() // D
+    g_out = torch.randn_like(z)
+    zt = z.detach().clone().requires_grad_(True)
+    res = {}
+    for name, kw in (("overlapped", dict(sync=True, overlap=True)), ("serial", dict(sync=True, overlap=False)),
+                     ("no_allreduce", dict(sync=False))):
+        if world == 1 and name != "no_allreduce":
+            continue
+        vq = EMAVectorQuantizer(K, D, 0.25, decay=0.99, search_mode=args.search_mode, **kw).to(dev).train()
+        with torch.no_grad():
+            vq.embedding.weight.copy_(cb)
+            vq.ema_sum.copy_(cb)
+            vq.ema_count.fill_(1.0)
+
+        def tstep():
+            zt.grad = None
+            z_q, loss, _ = vq(zt)
+            torch.autograd.backward([z_q, loss], [g_out, torch.ones_like(loss)])
+
+        for _ in range(max(3, args.warmup)):
+            tstep()
+        vq.sync_codebook()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            tstep()
+        vq.sync_codebook()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = float(t)
+        if world > 1 and name == "overlapped":      # every rank must hold the same codebook after the same steps
+            w = vq.embedding.weight.detach()
+            lo, hi = w.clone(), w.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            res["codebooks_identical_across_ranks"] = bool(torch.equal(lo, hi))
+        del vq
+    main = res.get("overlapped", res["no_allreduce"])
+    rec = {"workload": "training-mode quantizer at the c2 shape per GPU: fwd + STE backward (dz) + loss + EMA codebook update",
+           "ms_per_step": main, "value": n_lat * world / (main * 1e-3), "unit": UNIT, "n_gpus": world,
+           "ms_per_step_by_variant": res, "allreduce_bytes": (K * D + K) * 4 if world > 1 else 0,
+           "collective": "one NCCL all-reduce (SUM, FP32) of [resid K*D | counts K] per step, issued async after the forward, "
+                         "waited for at the end of the quantizer's backward" if world > 1 else "none (one rank)"}
+    if world > 1:
+        rec["exposed_allreduce_us"] = (res["overlapped"] - res["no_allreduce"]) * 1e3
+        rec["exposed_allreduce_us_if_serial"] = (res["serial"] - res["no_allreduce"]) * 1e3
+    return rec
+
+
 _ORIGINAL_AFFINITY = None
 
 
@@ -237,6 +425,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--search-mode", default="auto", choices=["auto", "tensor", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records of the default line (train, roofline_k16384, index_match, 8x8-layout HBM kernels)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's local CPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -310,9 +500,8 @@ def main():
         out = step(z)      # (same object lifetime pattern as the timed loop: the caching allocator reaches
                            #  its steady state here, not inside the timed region)
     barrier()
-    # timed region: CUDA events on the launching stream; the dominant kernel (screen) is additionally
-    # bracketed by its own events so its launch duration is measured live inside the same region
-    ops.PROFILER.reset(timing={"ccvsq_screen", "ccvsq_search_exact"})
+    # timed region, pass A: exactly the product's launch chain (no events inside it) -> `value`
+    ops.PROFILER.reset(timing=False)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_host0 = time.perf_counter()
@@ -324,6 +513,18 @@ def main():
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = ops.PROFILER.launches
+    # pass B: the same K steps again with the dominant kernel (screen) bracketed by its own CUDA events, recorded
+    # inside the composite call on the launching stream -> `roofline` (the two cudaEventRecords sit inside the
+    # programmatic-dependent-launch chain, so this pass is NOT the one `value` comes from)
+    ops.PROFILER.reset(timing={"ccvsq_screen", "ccvsq_search_exact"})
+    evb0, evb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    evb0.record()
+    for _ in range(args.steps):
+        out = step(z)
+    evb1.record()
+    barrier()
+    ms_total_b = evb0.elapsed_time(evb1)
     prof_main = ops.PROFILER.summary()
     # keep the GPU under the same load until nvidia-smi has produced a few samples (its period is 100 ms,
     # a short timed region can end before the first one)
@@ -430,6 +631,11 @@ def main():
                    + ("; frame-chunked x%d (ccvs_b200.pipeline.HostQuantizePipeline): H2D of chunk c+1 overlaps the "
                       "quantization of chunk c" % pipe.n_chunks if pipe is not None else "")}
 
+    # ---------------- training-mode sub-record (every rank: it contains the design's only collective) ----------------
+    train_rec = None
+    if args.workload == "c2" and not args.no_extras:
+        train_rec = train_record(args, dev, world, cb, z.detach(), barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -514,10 +720,20 @@ def main():
                    "search_mode": args.search_mode, "screen_operands": "bf16 (fp32 accumulate), fp32 rescoring",
                    "l2": f"inputs larger than L2 ({z.numel() * 4 / 2**20:.0f} MiB of latents per step)",
                    "parallelism": f"frame-sharded x{world}, codebook replicated, no data-path collective",
-                   "host_affinity": host_affinity},
+                   "host_affinity": host_affinity,
+                   "timing": "value: K steps of the product launch chain between two CUDA events (no events inside); "
+                             "roofline: a second pass of the same K steps with the screen kernel bracketed by events"},
         "e2e": e2e, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "kernel_breakdown": breakdown, "hbm_kernels": extra, "small_batch": small,
+        "ms_per_step_with_kernel_events": ms_total_b / args.steps,
+        "train": train_rec,
     }
+    if args.workload == "c2" and world == 1 and not args.no_extras:
+        # north_star targets that the default workload does not exercise (rank 0, one GPU)
+        torch.cuda.empty_cache()
+        line["roofline_k16384"], line["hbm_kernels_8x8"] = k16384_records(dev, args.search_mode, peaks())
+        if not args.no_cpu_baseline:
+            line["index_match"] = index_match_record(dev, args.search_mode)
     print_result(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

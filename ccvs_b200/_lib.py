@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CCVSQ_LIB") or os.path.join(_HERE, "lib", "libccvsq.so")   # (override: A/B runs of two builds)
@@ -44,6 +44,7 @@ class ForwardArgs(Structure):
     """struct ccvsq_forward_args — see include/ccvsq.h."""
 
     _fields_ = [
+        ("struct_size", c_uint32), ("flags", c_uint32),
         ("z", c_void_p), ("lay", Layout), ("E", c_void_p), ("K", c_int32), ("beta", c_float),
         ("search_mode", c_int32), ("n_cand", c_int32), ("margin_tau", c_float), ("exact_fallback", c_int32),
         ("indices_only", c_int32), ("prepare", c_int32),
@@ -55,6 +56,12 @@ class ForwardArgs(Structure):
     ]
 
 
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        self.struct_size = ctypes.sizeof(ForwardArgs)     # checked by the library (stale bindings are rejected)
+
+
+ABI_MAJOR = 2
 HEADER_INTS = 16
 SEARCH_MODES = {"auto": 0, "tensor": 1, "exact": 2}
 
@@ -117,8 +124,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.ccvsq_version() // 100 != 1:
-        raise RuntimeError(f"libccvsq ABI version {lib.ccvsq_version()} is not 1.x")
+    if lib.ccvsq_version() // 100 != ABI_MAJOR:
+        raise RuntimeError(f"libccvsq ABI version {lib.ccvsq_version()} is not {ABI_MAJOR}.x")
     _lib = lib
     return lib
 

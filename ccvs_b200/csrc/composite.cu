@@ -45,6 +45,10 @@ extern "C" uint64_t ccvsq_forward_workspace_bytes(int64_t N, int K, int D, int s
 
 extern "C" int ccvsq_quantize_forward(const ccvsq_forward_args* a, void* stream) {
   CCVSQ_REQUIRE(a, CCVSQ_NULL_POINTER, "quantize_forward: null args");
+  CCVSQ_REQUIRE(a->struct_size == sizeof(ccvsq_forward_args), CCVSQ_BAD_SHAPE,
+                "quantize_forward: args.struct_size=%u but this library's ccvsq_forward_args has %zu bytes (ABI %d): the "
+                "caller's struct definition is stale", a->struct_size, sizeof(ccvsq_forward_args), CCVSQ_VERSION);
+  CCVSQ_REQUIRE(a->flags == 0, CCVSQ_BAD_SHAPE, "quantize_forward: args.flags=%u (reserved, must be 0)", a->flags);
   CCVSQ_REQUIRE(a->z && a->E && a->header && a->idx, CCVSQ_NULL_POINTER, "quantize_forward: z, E, header and idx are required");
   CCVSQ_REQUIRE(a->K > 0, CCVSQ_BAD_SHAPE, "quantize_forward: K=%d", a->K);
   CCVSQ_REQUIRE(a->search_mode >= CCVSQ_SEARCH_AUTO && a->search_mode <= CCVSQ_SEARCH_EXACT, CCVSQ_BAD_SHAPE,

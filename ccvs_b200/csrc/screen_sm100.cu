@@ -399,7 +399,8 @@ __device__ __noinline__ void finalize_row(uint32_t sc_base, uint32_t co_base, ui
   }
   const uint8_t flag = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped_max >= thr ? 2 : 0));
   const bool final_row = within == 1 && flag == 0;
-  if (out.idx) out.idx[row] = best_i;
+  // (a row of NaN / Inf latents lists nothing: every returned index stays inside [0, K) like torch.argmin's)
+  if (out.idx) out.idx[row] = best_i < 0 ? 0 : best_i;
   if (final_row && !out.dbg_cand) return;
 
   int slot = -1;

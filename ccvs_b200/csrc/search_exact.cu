@@ -183,7 +183,9 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
       __threadfence();
       for (int64_t i = tid; i < total_rows; i += XT) {
         const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(keys + i);
-        idx[row_list[i]] = (int64_t)(key & 0xffffffffull);
+        // (a row whose distances are all NaN / +inf never beats the all-ones key: give it code 0, in range like
+        //  torch.argmin's answer, instead of 2^32 - 1)
+        idx[row_list[i]] = key == ~0ull ? 0 : (int64_t)(key & 0xffffffffull);
       }
     }
   }

@@ -63,8 +63,8 @@ def all_reduce_stats(resid: torch.Tensor, counts: torch.Tensor, sq_err: torch.Te
 def ema_stats_buffer(K: int, D: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
     """Packed buffer for the EMA statistics exchange, [resid: K*D | counts: K] fp32, and the [K, D] view the assign
     pass accumulates the residual sums into directly (no pack copy)."""
-    buf = torch.empty(K * D + K, dtype=torch.float32, device=device)
-    return buf, buf[: K * D].view(K, D)
+    buf = torch.empty(K * D + K, dtype=torch.float32, device=device)   # (the forward zeroes the resid part; an empty
+    return buf, buf[: K * D].view(K, D)                                 #  shard zeroes all of it before the collective)
 
 
 def reduce_ema_stats(buf: torch.Tensor, counts: torch.Tensor, K: int, D: int,
@@ -74,6 +74,25 @@ def reduce_ema_stats(buf: torch.Tensor, counts: torch.Tensor, K: int, D: int,
     buf[K * D:].copy_(counts)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf[: K * D].view(K, D), buf[K * D:].round().to(torch.int32)
+
+
+def start_reduce_ema_stats(buf: torch.Tensor, counts: torch.Tensor, K: int, D: int,
+                           group: Optional[dist.ProcessGroup] = None):
+    """First half of `reduce_ema_stats`: pack the counts and ISSUE the all-reduce without making the current stream
+    wait for it (NCCL runs it on its own stream, ordered after the work already enqueued on the current one).
+    Returns the work handle (None when there is nothing to reduce)."""
+    buf[K * D:].copy_(counts)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return None
+
+
+def finish_reduce_ema_stats(work, buf: torch.Tensor, K: int, D: int):
+    """Second half: the current stream waits for the collective (no host block with NCCL); returns
+    (resid [K, D] view, counts int32 [K])."""
+    if work is not None:
+        work.wait()
     return buf[: K * D].view(K, D), buf[K * D:].round().to(torch.int32)
 
 

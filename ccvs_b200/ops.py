@@ -18,6 +18,14 @@ from ._lib import Layout
 
 _L = _lib.load()  # fail loudly at import time if the extension is missing
 
+# Screening margin in units of 2^-8 * ||z|| * max||e|| (see ccvsq_screen).  Both operands of every product are rounded
+# to BF16 (relative error <= 2^-8 each), so ONE score errs by at most 2 * 2^-8 * sum_j |z_j e_kj| <= 2^-7 ||z|| ||e_k||,
+# and the FP32 winner can trail the BF16 maximum by at most the error of TWO scores: 4 * 2^-8 * ||z|| max||e||.
+# tau = 4 is therefore the PROVEN bound (the true winner always survives the screen, up to FP32 accumulation noise
+# ~2^-22 ||z|| ||e||); tau = 1 is ~30 standard deviations of the rounding noise for dense D = 256 vectors but can be
+# beaten by adversarial inputs (tests/test_gpu_parity.py::test_adversarial_margin).
+DEFAULT_MARGIN_TAU = 4.0
+
 # kernels enqueued by each entry point (ccvsq_prepare_codebook: + one 4-byte memset node)
 _KERNELS_PER_CALL = {
     "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_trace": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
@@ -55,8 +63,26 @@ class Profiler:
 PROFILER = Profiler()
 
 
+class _StreamArg:
+    """The stream argument of an entry point plus the device it belongs to: `_call` makes that device current for
+    the duration of the C call when it is not already (kernel launches, cudaFuncSetAttribute and cudaGetDevice inside
+    the library act on the thread's CURRENT device, while pointers and stream come from the tensor's device)."""
+
+    __slots__ = ("ptr", "index")
+
+    def __init__(self, ptr, index):
+        self.ptr = ptr
+        self.index = index
+
+
 def _call(name: str, *args) -> None:
     fn = getattr(_L, name)
+    if args and isinstance(args[-1], _StreamArg):
+        st = args[-1]
+        args = args[:-1] + (st.ptr,)
+        if st.index is not None and st.index != torch.cuda.current_device():
+            with torch.cuda.device(st.index):
+                return _call(name, *args)
     if PROFILER.timing is True or (PROFILER.timing and name in PROFILER.timing):
         s = torch.cuda.Event(enable_timing=True)
         e = torch.cuda.Event(enable_timing=True)
@@ -89,8 +115,9 @@ def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr())
 
 
-def _stream(dev: torch.device) -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+def _stream(dev: torch.device) -> _StreamArg:
+    dev = torch.device(dev)
+    return _StreamArg(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream), dev.index)
 
 
 def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
@@ -201,7 +228,7 @@ def _new_queue(N: int, n_cand: int, dev) -> ScreenQueue:
                        torch.empty(N, n_cand, dtype=torch.int32, device=dev), torch.empty(N, dtype=torch.uint8, device=dev))
 
 
-def screen(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, margin_tau: float = 1.0):
+def screen(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, margin_tau: float = DEFAULT_MARGIN_TAU):
     """tcgen05 screening GEMM with fused candidate selection.  Returns (idx int64 [N], ScreenQueue)."""
     dev = z.device
     N = lay.rows
@@ -212,7 +239,7 @@ def screen(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, 
     return idx, q
 
 
-def screen_trace(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, margin_tau: float = 1.0):
+def screen_trace(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, margin_tau: float = DEFAULT_MARGIN_TAU):
     """ccvsq_screen with the pipeline timeline (see ccvsq.h): returns (idx, queue, trace int64 [148, 32, 8])."""
     dev = z.device
     N = lay.rows
@@ -235,7 +262,7 @@ class ScreenDebug:
     scores: Optional[torch.Tensor]   # [N, codebook_rows(K)] fp32
 
 
-def screen_debug(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, margin_tau: float = 1.0,
+def screen_debug(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, n_cand: int = 4, margin_tau: float = DEFAULT_MARGIN_TAU,
                  cta_group: int = 2, dump_scores: bool = False) -> ScreenDebug:
     """Diagnostic variant: candidate lists / margins for every row, optionally the full score matrix."""
     dev = z.device
@@ -276,7 +303,7 @@ def rescore(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, idx: torch.Tenso
 
 
 def search(z: torch.Tensor, lay: Layout, cb: PreparedCodebook, mode: str = "auto", n_cand: int = 4,
-           margin_tau: float = 1.0, exact_fallback: bool = True) -> torch.Tensor:
+           margin_tau: float = DEFAULT_MARGIN_TAU, exact_fallback: bool = True) -> torch.Tensor:
     """Nearest-code indices, int64 [N].  mode: 'auto' | 'tensor' | 'exact'."""
     _req(z, torch.float32, "z")
     if mode not in ("auto", "tensor", "exact"):
@@ -420,7 +447,7 @@ class ForwardOut:
 
 
 def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: float, mode: str = "auto", n_cand: int = 4,
-                     margin_tau: float = 1.0, exact_fallback: bool = True, cb: Optional[PreparedCodebook] = None,
+                     margin_tau: float = DEFAULT_MARGIN_TAU, exact_fallback: bool = True, cb: Optional[PreparedCodebook] = None,
                      indices_only: bool = False, want_resid: bool = False,
                      resid_out: Optional[torch.Tensor] = None) -> ForwardOut:
     """The whole forward of quantize.py:32-74 in one call of the C ABI (ccvsq_quantize_forward).

@@ -27,34 +27,83 @@ from . import ops
 from ._lib import Layout
 
 
-class LazyOneHot:
-    """Stand-in for the reference's dense `min_encodings` [N, K] (quantize.py:51-52).
+class LazyOneHot(torch.Tensor):
+    """The reference's dense `min_encodings` [N, K] (quantize.py:51-52) as a tensor that is materialised on first use.
 
-    No reference caller reads it; at the stress config it would be 128 GiB per GPU.
-    `.dense()` builds the real tensor on demand; `.shape`, `.dtype`, `.device` answer without
-    allocating.
+    No reference caller reads it and at the stress config it would be 128 GiB per GPU, so the forward
+    returns this storage-less `torch.Tensor` subclass: `.shape`, `.dtype`, `.device`, `.size()`, `isinstance(x,
+    torch.Tensor)` answer without allocating; `x.sum(0)` / `x.mean(0)` / `torch.mean(x, dim=0)` (what the
+    reference itself does with it, quantize.py:67) are answered from a bincount of the indices; ANY other torch
+    operation receives the real dense tensor (`.dense()`, built once by scatter and cached), so an unmodified
+    caller sees exactly the reference's tensor.
     """
+
+    @staticmethod
+    def __new__(cls, indices: torch.Tensor, n_e: int, dtype: torch.dtype):
+        return torch.Tensor._make_wrapper_subclass(cls, (indices.shape[0], n_e), dtype=dtype, device=indices.device,
+                                                   requires_grad=False)
 
     def __init__(self, indices: torch.Tensor, n_e: int, dtype: torch.dtype):
         self.indices = indices
         self.n_e = n_e
-        self.dtype = dtype
-
-    @property
-    def shape(self):
-        return torch.Size((self.indices.shape[0], self.n_e))
-
-    @property
-    def device(self):
-        return self.indices.device
+        self._dense: Optional[torch.Tensor] = None
 
     def dense(self) -> torch.Tensor:
-        out = torch.zeros(self.indices.shape[0], self.n_e, dtype=self.dtype, device=self.indices.device)
-        out.scatter_(1, self.indices.view(-1, 1), 1)
-        return out
+        if self._dense is None:
+            out = torch.zeros(self.indices.shape[0], self.n_e, dtype=self.dtype, device=self.indices.device)
+            out.scatter_(1, self.indices.view(-1, 1), 1)
+            self._dense = out
+        return self._dense
+
+    def usage(self) -> torch.Tensor:
+        """Column sums [K] (= min_encodings.sum(0)) without the dense matrix."""
+        return torch.bincount(self.indices.view(-1), minlength=self.n_e).to(self.dtype)
 
     def __repr__(self):
-        return f"LazyOneHot(shape={tuple(self.shape)}, device={self.device})"
+        return f"LazyOneHot(shape={tuple(self.shape)}, dtype={self.dtype}, device={self.device})"
+
+    _META = {"shape", "dtype", "device", "layout", "ndim", "requires_grad", "is_cuda", "is_leaf", "grad", "grad_fn",
+             "names", "is_sparse", "is_quantized", "is_meta", "_version", "output_nr", "is_cpu"}
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        name = getattr(func, "__name__", "")
+        owner = getattr(getattr(func, "__self__", None), "__name__", "")
+        with torch._C.DisableTorchFunctionSubclass():
+            if name == "__get__" and owner in cls._META:          # attribute reads: answered by the wrapper itself
+                return func(*args, **kwargs)
+            if name in ("size", "dim", "numel", "nelement", "element_size", "is_floating_point", "is_contiguous",
+                        "__repr__", "__len__", "get_device") and not kwargs:
+                return func(*args)
+            if name in ("sum", "mean") and isinstance(args[0], LazyOneHot):
+                rest = args[1:]
+                dim = kwargs.get("dim", kwargs.get("axis", rest[0] if rest else None))
+                extra = {k: v for k, v in kwargs.items() if k not in ("dim", "axis")}
+                if dim in (0, (0,), [0], -2, (-2,)) and len(rest) <= 1 and not extra:
+                    u = args[0].usage()
+                    return u if name == "sum" else u / args[0].shape[0]
+
+            def unwrap(x):
+                if isinstance(x, LazyOneHot):
+                    return x.dense()
+                if isinstance(x, (list, tuple)):
+                    return type(x)(unwrap(v) for v in x)
+                return x
+
+            return func(*unwrap(args), **{k: unwrap(v) for k, v in kwargs.items()})
+
+    @classmethod
+    def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
+        """Anything that reaches the dispatcher without passing __torch_function__ (C++ callers) gets the dense tensor."""
+        def unwrap(x):
+            if isinstance(x, LazyOneHot):
+                return x.dense()
+            if isinstance(x, (list, tuple)):
+                return type(x)(unwrap(v) for v in x)
+            return x
+
+        return func(*unwrap(args), **{k: unwrap(v) for k, v in (kwargs or {}).items()})
 
 
 class _QuantizeFn(torch.autograd.Function):
@@ -76,6 +125,7 @@ class _QuantizeFn(torch.autograd.Function):
         module._last_resid = out.resid        # per-code residual sums for the EMA update (None unless asked for)
         ctx.lay = lay
         ctx.beta = module.beta
+        ctx.module = module
         # the EMA variant rewrites the codebook in place right after forward: keep the version the
         # indices were computed with for backward
         ctx.save_for_backward(z, weight.detach().clone() if module._inplace_codebook_update else weight, idx)
@@ -95,6 +145,7 @@ class _QuantizeFn(torch.autograd.Function):
             return None, None, None
         g = None if (g_zq is None or not want_dz) else g_zq.to(torch.float32).contiguous()
         dz, dE = ops.quantize_backward(z, lay, weight, idx, g, g_loss, ctx.beta, want_dz, want_dE)
+        ctx.module._after_backward()
         return dz, dE, None
 
 
@@ -166,12 +217,13 @@ class VectorQuantizer(nn.Module):
     - search_mode: 'auto' (tensor-core screen + FP32 rescoring when the shape allows, exact FP32
       kernel otherwise), 'tensor', or 'exact'
     - n_cand: candidate slots per latent kept by the screen (<= 8)
-    - margin_tau: screening margin in units of 2^-8 * ||z|| * max||e||
+    - margin_tau: screening margin in units of 2^-8 * ||z|| * max||e|| (default 4 = the proven worst-case bound for the
+      difference of two BF16-operand scores, ops.DEFAULT_MARGIN_TAU)
     - exact_fallback: rows with more than n_cand codes inside the margin are re-searched exactly
     """
 
     def __init__(self, n_e, e_dim, beta, mult=1, normalize=False, *, search_mode: str = "auto", n_cand: int = 4,
-                 margin_tau: float = 1.0, exact_fallback: bool = True):
+                 margin_tau: float = ops.DEFAULT_MARGIN_TAU, exact_fallback: bool = True):
         super().__init__()
         self.n_e = n_e
         assert e_dim % mult == 0
@@ -193,6 +245,13 @@ class VectorQuantizer(nn.Module):
         self._inplace_codebook_update = False
         self.last_counts: Optional[torch.Tensor] = None   # int32 [K] usage of the last forward
 
+    def _after_backward(self):
+        """Called by `_QuantizeFn.backward` once its kernels are enqueued (the EMA variant completes its deferred
+        statistics exchange here)."""
+        sync = getattr(self, "sync_codebook", None)
+        if sync is not None:
+            sync()
+
     # -- codebook side data (||e||^2, BF16 shadow, bias).  Rebuilt on EVERY call by default: the
     # reference's Polyak averaging writes `param.data` in place (quantized_video_model.py:962-964),
     # which does not bump the autograd version counter, so no cheap staleness test exists.  The
@@ -202,16 +261,19 @@ class VectorQuantizer(nn.Module):
         """The frozen side data if it still belongs to the live parameter, else None (= rebuild in-call)."""
         cb = self._cb
         w = self.embedding.weight
-        if cb is not None and cb.ptr == w.data_ptr() and cb.weight.device == w.device:
+        if cb is not None and cb.ptr == w.data_ptr() and cb.weight.device == w.device and cb.version == w._version:
             return cb
+        self._cb = None        # moved, or written in place through autograd-visible ops (optimizer.step, copy_, ...)
         return None
 
     def _prepared(self) -> ops.PreparedCodebook:
         return self._cb_cached() or ops.prepare_codebook(self.embedding.weight)
 
     def freeze_codebook(self):
-        """Cache the codebook side data until `unfreeze_codebook()` (caller promises not to
-        modify `embedding.weight` in between)."""
+        """Cache the codebook side data until `unfreeze_codebook()`.  The cache is dropped automatically when the
+        parameter moves or its autograd version changes (optimizer steps, `copy_`, `load_state_dict`) and by
+        `accumulate_from`; writes through `.data` / `.detach()` views made behind the module's back are NOT visible
+        (no version bump, quantized_video_model.py:962-964): the caller promises not to do that while frozen."""
         self._cb = ops.prepare_codebook(self.embedding.weight)
         return self
 
@@ -287,9 +349,11 @@ class VectorQuantizer(nn.Module):
         """Indices only (what QVidModel.encode keeps, quantized_video_model.py:798-799): int64 [N]."""
         if not z.is_cuda:
             raise RuntimeError("CUDA only; there is no CPU fallback")
-        z = z.contiguous()
-        if z.dtype != torch.float32:
+        if z.dtype in (torch.float16, torch.bfloat16):
+            z = z.float()            # same upcast as forward()
+        elif z.dtype != torch.float32:
             raise TypeError(f"the reference quantizer is FP32 end to end; got {z.dtype}")
+        z = z.contiguous()
         if z.numel() == 0:
             return torch.empty(0, dtype=torch.int64, device=z.device)
         lay = ops.layout_of(z.shape, self.e_dim, self.mult)
@@ -302,6 +366,7 @@ class VectorQuantizer(nn.Module):
         `acc(self.net_q_ema, self.net_q, decay)`): self.embedding.weight <- decay*self + (1-decay)*live, written
         through `.data` in place exactly like the reference (no autograd version bump)."""
         ops.polyak(self.embedding.weight.data, live.embedding.weight.data, decay)
+        self._cb = None         # the `.data` write is invisible to the version check of a frozen codebook
         return self
 
     def embed_tokens(self, code: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor):
@@ -461,35 +526,75 @@ class EMAVectorQuantizer(VectorQuantizer):
         N_k <- g N_k + (1-g) n_k ;  m_k <- g m_k + (1-g) S_k ;  E_k <- m_k / smooth(N_k)
     """
 
-    def __init__(self, n_e, e_dim, beta, mult=1, *, decay: float = 0.99, eps: float = 1e-5, sync: bool = True, **kw):
+    def __init__(self, n_e, e_dim, beta, mult=1, *, decay: float = 0.99, eps: float = 1e-5, sync: bool = True,
+                 overlap: bool = True, **kw):
         super().__init__(n_e, e_dim, beta, mult=mult, normalize=False, **kw)
         self.decay = decay
         self.eps = eps
         self.sync = sync
+        self.overlap = overlap            # hide the statistics all-reduce under the backward pass (see forward)
         self.embedding.weight.requires_grad_(False)
         self._inplace_codebook_update = True
+        self._last_resid = None
+        self._pending = None              # (work handle | None, packed buffer) of a deferred all-reduce + EMA update
         self.register_buffer("ema_count", torch.zeros(n_e))
         self.register_buffer("ema_sum", self.embedding.weight.detach().clone())
 
     def forward(self, z):
-        # the per-code residual sums of the EMA update ride on the assign pass of the forward (one read of z); with
-        # several ranks they are accumulated straight into the packed buffer of the one all-reduce
+        """Training forward = the reference forward + EMA statistics.  The per-code residual sums ride on the assign pass
+        (one read of z); with several ranks they are accumulated straight into the packed buffer of ONE all-reduce.
+
+        Overlap (`overlap=True`, several ranks, autograd on): the all-reduce is issued asynchronously right after the
+        forward's kernels; the wait and the in-place EMA update of the codebook are deferred to the end of this
+        module's backward (`_QuantizeFn.backward`), which works on the codebook copy saved by the forward — so the
+        collective runs on NCCL's stream under everything between this forward and that backward (decoder forward /
+        backward, the dz kernel) instead of sitting serially in front of them.  The update is flushed earlier by
+        anything that reads the codebook through this module (next forward, embed_code, sync_codebook, state_dict)."""
+        self.sync_codebook()
         buf = None
         self._want_resid = self.training
-        if self.training and self.sync and vq_dist.world_info()[1] > 1:
+        world = vq_dist.world_info()[1]
+        if self.training and self.sync and world > 1:
             buf, self._resid_out = vq_dist.ema_stats_buffer(self.n_e, self.e_dim, z.device)
         try:
             out = super().forward(z)
         finally:
             self._want_resid = False
             self._resid_out = None
-        if self.training:
-            with torch.no_grad():
-                w = self.embedding.weight
-                resid = self._last_resid
-                self._last_resid = None
-                counts = self.last_counts          # per-code usage from the forward's assign kernel
-                if buf is not None:
-                    resid, counts = vq_dist.reduce_ema_stats(buf, counts, self.n_e, self.e_dim)
-                ops.ema_update(w, self.ema_count, self.ema_sum, resid, counts, self.decay, self.eps)
+        if not self.training:
+            return out
+        with torch.no_grad():
+            resid, self._last_resid = self._last_resid, None
+            counts = self.last_counts          # per-code usage from the forward's assign kernel (zeros for an empty shard)
+            if buf is None:
+                if z.numel() == 0:
+                    return out                 # nothing was assigned: the codebook keeps its state
+                ops.ema_update(self.embedding.weight, self.ema_count, self.ema_sum, resid, counts, self.decay, self.eps)
+                return out
+            if z.numel() == 0:
+                buf.zero_()                    # an empty shard still joins the collective, with zero statistics
+            work = vq_dist.start_reduce_ema_stats(buf, counts, self.n_e, self.e_dim)
+            self._pending = (work, buf)
+            deferred = self.overlap and torch.is_grad_enabled() and out[0].requires_grad
+            if not deferred:
+                self.sync_codebook()
         return out
+
+    @torch.no_grad()
+    def sync_codebook(self):
+        """Complete a deferred statistics exchange: the current stream waits for the all-reduce, then the EMA update
+        rewrites the codebook in place.  No-op when nothing is pending."""
+        if self._pending is None:
+            return
+        work, buf = self._pending
+        self._pending = None
+        resid, counts = vq_dist.finish_reduce_ema_stats(work, buf, self.n_e, self.e_dim)
+        ops.ema_update(self.embedding.weight, self.ema_count, self.ema_sum, resid, counts, self.decay, self.eps)
+
+    def embed_code(self, code, channel_major_hw=None, table=None):
+        self.sync_codebook()
+        return super().embed_code(code, channel_major_hw=channel_major_hw, table=table)
+
+    def state_dict(self, *args, **kw):
+        self.sync_codebook()
+        return super().state_dict(*args, **kw)

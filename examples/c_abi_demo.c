@@ -88,6 +88,7 @@ int main(void) {
   /* forward: quantize.py:32-74 in one call */
   ccvsq_forward_args a;
   memset(&a, 0, sizeof(a));
+  a.struct_size = (uint32_t)sizeof(a);   /* lets the library reject a binding built against another header */
   a.z = dz; a.lay = lay; a.E = dE; a.K = K; a.beta = 0.25f;
   a.search_mode = CCVSQ_SEARCH_AUTO; a.n_cand = 4; a.margin_tau = 1.0f; a.exact_fallback = 1;
   a.header = dhdr; a.workspace = dws; a.workspace_bytes = ws_bytes;

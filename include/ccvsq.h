@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CCVSQ_VERSION 103 /* major*100 + minor */
+#define CCVSQ_VERSION 200 /* major*100 + minor; 2.x: ccvsq_forward_args starts with struct_size */
 
 typedef enum ccvsq_status {
   CCVSQ_OK = 0,
@@ -240,6 +240,10 @@ int ccvsq_ema_update(float* E, float* n_ema, float* sum_ema, const float* resid,
 #define CCVSQ_SEARCH_EXACT 2
 
 typedef struct ccvsq_forward_args {
+  uint32_t struct_size;    /* = sizeof(ccvsq_forward_args) of the header the caller was built against: a binding whose
+                              struct layout is stale (a missing trailing field) is rejected with CCVSQ_BAD_SHAPE instead
+                              of being read out of bounds */
+  uint32_t flags;          /* reserved, must be 0 */
   const float* z;
   ccvsq_layout lay;
   const float* E;

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_version():
-    assert _lib.load().ccvsq_version() == 103
+    assert _lib.load().ccvsq_version() == 200
 
 
 def test_argument_validation_without_gpu():
@@ -56,6 +56,14 @@ def test_composite_argument_validation_without_gpu():
     null = ctypes.c_void_p(0)
     assert lib.ccvsq_quantize_forward(None, null) == -5
     a = _lib.ForwardArgs()
+    assert a.struct_size == ctypes.sizeof(_lib.ForwardArgs)
+    a.struct_size -= 8                                                        # a stale binding (one trailing field short)
+    assert lib.ccvsq_quantize_forward(ctypes.byref(a), null) == -1
+    assert b"struct_size" in lib.ccvsq_last_error()
+    a.struct_size += 8
+    a.flags = 4
+    assert lib.ccvsq_quantize_forward(ctypes.byref(a), null) == -1            # reserved flag bits
+    a.flags = 0
     assert lib.ccvsq_quantize_forward(ctypes.byref(a), null) == -5            # z / E / header / idx missing
     a.z = a.E = a.header = a.idx = 16
     a.lay = _lib.Layout(4, 64, 16, 1)
@@ -78,8 +86,39 @@ def test_composite_argument_validation_without_gpu():
 
 
 def test_layout_struct_matches_header():
-    assert ctypes.sizeof(_lib.ForwardArgs) == 176
-    assert _lib.ForwardArgs.resid.offset == 168
-    assert _lib.ForwardArgs.lay.offset == 8 and _lib.ForwardArgs.e_sq.offset == 72 and _lib.ForwardArgs.idx.offset == 120
+    assert ctypes.sizeof(_lib.ForwardArgs) == 184
+    assert _lib.ForwardArgs.struct_size.offset == 0 and _lib.ForwardArgs.z.offset == 8
+    assert _lib.ForwardArgs.resid.offset == 176
+    assert _lib.ForwardArgs.lay.offset == 16 and _lib.ForwardArgs.e_sq.offset == 80 and _lib.ForwardArgs.idx.offset == 128
     assert ctypes.sizeof(_lib.Layout) == 24     # int64 + 3 x int32 (+4 pad)
     assert _lib.Layout.G.offset == 0 and _lib.Layout.C.offset == 8 and _lib.Layout.mult.offset == 16
+
+
+def integration_stub_namespace():
+    """Execute the ctypes stub printed in INTEGRATION.md section 2 verbatim (cwd = repo root, as the text assumes)."""
+    root = os.path.dirname(_lib.HEADER_PATH.rstrip("/")).rsplit("/include", 1)[0]
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    m = re.search(r"```python\n(# --- ctypes stub.*?)```", text, flags=re.S)
+    assert m, "INTEGRATION.md lost its ctypes stub block"
+    ns = {"__name__": "integration_stub"}
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        exec(compile(m.group(1), "INTEGRATION.md:stub", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    return ns
+
+
+def test_integration_stub_matches_the_header():
+    """The binding a maintainer would copy from INTEGRATION.md has the library's struct layout (round 1 shipped a stub
+    one field short: the library would have read past the caller's struct)."""
+    ns = integration_stub_namespace()
+    stub, ours = ns["ForwardArgs"], _lib.ForwardArgs
+    assert ctypes.sizeof(stub) == ctypes.sizeof(ours)
+    assert [(n, getattr(stub, n).offset, getattr(stub, n).size) for n, _ in stub._fields_] == \
+           [(n, getattr(ours, n).offset, getattr(ours, n).size) for n, _ in ours._fields_]
+    assert ctypes.sizeof(ns["Layout"]) == ctypes.sizeof(_lib.Layout)
+    # a zero-initialised stub struct without struct_size is rejected, not read out of bounds
+    a = stub()
+    assert ns["lib"].ccvsq_quantize_forward(ctypes.byref(a), None) == -1

@@ -1,0 +1,271 @@
+"""GPU parity hardening: adversarial inputs for the BF16 screening margin, property tests (hypothesis) and
+non-finite latents.  Everything goes through the C ABI (ccvs_b200.ops / VectorQuantizer) and is checked against
+the CPU oracle (oracle/vq_oracle.py) on the same inputs.
+
+Parity rules as in tests/test_gpu_parity.py: indices equal to the oracle's except documented near-ties (oracle
+FP32 distance gap <= 1e-6 relative); z_q / embed_code bit-exact given equal indices; loss within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import vq_oracle
+from ccvs_b200 import VectorQuantizer, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+# ------------------------------------------------------------------------------------------------
+# adversarial margin: operands at BF16 rounding midpoints, energy concentrated in two channels
+# ------------------------------------------------------------------------------------------------
+def _bf16(x):
+    return torch.as_tensor(x, dtype=torch.float32).to(torch.bfloat16).to(torch.float64)
+
+
+def _midpoints(direction, rng, n):
+    """FP32 values exactly halfway between two neighbouring BF16 numbers in [1.5, 2) whose round-to-nearest-even
+    goes `direction` (+1 up, -1 down): the largest rounding error BF16 can make (2^-8 relative)."""
+    out = []
+    while len(out) < n:
+        m = int(rng.integers(64, 127))               # 7-bit mantissa of the lower neighbour
+        goes_up = (m & 1) == 1                       # ties to even: an odd lower neighbour rounds up
+        if goes_up == (direction > 0):
+            out.append(1.0 + (2 * m + 1) / 256.0)    # lower neighbour 1 + m/128, midpoint adds 2^-8
+    return np.array(out)
+
+
+def _round_up_midpoint_below(x):
+    """Largest BF16 midpoint <= x that rounds UP (1 + m/256 with m = 3 mod 4, times the binade of x)."""
+    e = int(np.floor(np.log2(x)))
+    m = int(np.floor((x / 2.0 ** e - 1.0) * 256.0))
+    while m % 4 != 3:
+        m -= 1
+    return None if m < 0 else (1.0 + m / 256.0) * 2.0 ** e
+
+
+def adversarial_case(D=64, rows_per_pair=8, seed=5):
+    """Rows and codes built so that the FP32 winner A of every row LOSES the BF16-rounded comparison against a
+    rival B by more than the tau = 1 margin: row = (x1 at channel 2p, x2 at channel 2p+1), A_p = a on channel 2p,
+    B_p = b on channel 2p+1.  x1 and a round DOWN (the score of A shrinks by ~2^-7 x1 a), x2 and b round UP (the
+    score of B grows by ~2^-7 x2 b); x2 is solved so that in exact arithmetic A still wins by a gap of at least
+    2e-4 of its distance (200 x the documented near-tie tolerance).
+    Returns z [N, D], codebook [K, D], and per row (BF16 deficit of the FP32 winner) / (margin at tau = 1)."""
+    rng = np.random.default_rng(seed)
+    pairs = D // 2
+    cb = np.zeros((2 * pairs, D), dtype=np.float64)
+    picks = []
+    for p in range(pairs):
+        rows = []
+        while len(rows) < rows_per_pair:                      # resample the pair until it yields enough rows
+            a, b = float(_midpoints(-1, rng, 1)[0]), float(_midpoints(+1, rng, 1)[0])
+            rows = []
+            for _ in range(400):
+                x1 = float(_midpoints(-1, rng, 1)[0])
+                sA = x1 * a - 0.5 * a * a
+                x2 = _round_up_midpoint_below((sA + 0.5 * b * b) / b)     # s_B just below s_A
+                if x2 is None:
+                    continue
+                gap = sA - (x2 * b - 0.5 * b * b)                          # exact-arithmetic lead of A
+                hA = float(_bf16(x1) * _bf16(a)) - 0.5 * a * a             # what the screen sees
+                hB = float(_bf16(x2) * _bf16(b)) - 0.5 * b * b
+                d_best = (x1 - a) ** 2 + x2 * x2                           # oracle distance of the winner
+                rows.append((x1, x2, gap, hB - hA, d_best))
+            rows = [r for r in rows if r[2] > 2e-4 * r[4]]
+            rows = sorted(set(rows), key=lambda r: -r[3])[:rows_per_pair]
+        cb[2 * p, 2 * p], cb[2 * p + 1, 2 * p + 1] = a, b
+        picks.append(rows)
+    emax = float(np.sqrt((cb ** 2).sum(1)).max())
+    z_rows, ratio = [], []
+    for p, rows in enumerate(picks):
+        for x1, x2, gap, deficit, _ in rows:
+            row = np.zeros(D)
+            row[2 * p], row[2 * p + 1] = x1, x2
+            z_rows.append(row)
+            ratio.append(deficit / (2.0 ** -8 * np.hypot(x1, x2) * emax))
+    z = torch.tensor(np.stack(z_rows), dtype=torch.float32)
+    return z, torch.tensor(cb, dtype=torch.float32), np.array(ratio)
+
+
+def test_adversarial_margin():
+    """tau = 1 (the round-1 default: a first-order bound for vectors with evenly spread energy) prunes the FP32
+    winner on these inputs; the shipped default (tau = 4, the proven bound for the difference of two scores whose
+    operands are BOTH rounded to BF16) must not."""
+    z, cb, ratio = adversarial_case()
+    assert np.median(ratio) > 1.15 and ratio.max() < 4.0      # inside the proven bound, mostly outside tau = 1
+    assert z.shape[0] >= 128                                    # the tensor path needs a full row tile
+    D = z.shape[1]
+    lay = ops.layout_of(z.shape, D, 1)
+    pcb = ops.prepare_codebook(cb.to(DEV))
+    zc = z.to(DEV)
+    ref = vq_oracle.nearest(z, cb)
+    exact = ops.search(zc, lay, pcb, mode="exact").cpu()
+    assert torch.equal(exact, ref)
+    assert bool((ref % 2 == 0).all())                           # the A codes win in FP32
+    # the old margin loses rows (this is what keeps the test adversarial) ...
+    idx1 = ops.search(zc, lay, pcb, mode="tensor", margin_tau=1.0).cpu()
+    missed = int((idx1 != ref).sum())
+    assert missed > 0, "construction no longer defeats tau = 1: strengthen it"
+    # ... the default does not
+    idx = ops.search(zc, lay, pcb, mode="tensor").cpu()
+    par = vq_oracle.classify_indices(idx, z, cb)
+    assert par.mismatch == 0 and par.exact == par.n, par
+    vq = VectorQuantizer(cb.shape[0], D, 0.25, search_mode="tensor").to(DEV)
+    assert vq.margin_tau == ops.DEFAULT_MARGIN_TAU >= 4.0
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+        _, _, (_, _, idm) = vq(zc)
+    assert torch.equal(idm.view(-1).cpu(), ref)
+
+
+@pytest.mark.parametrize("kind", ["one_hot_energy", "leaky_relu", "sparse_codes"])
+def test_concentrated_energy_latents(kind):
+    """Latents whose energy sits in a few channels (what a LeakyReLU encoder tail produces,
+    skip_autoencoder.py:346-349) against dense and sparse codebooks: zero mismatches outside documented
+    near-ties at the default margin, through the tensor-core path."""
+    g = torch.Generator().manual_seed(11)
+    N, K, D = 4096, 1024, 256
+    cb = torch.randn(K, D, generator=g)
+    if kind == "one_hot_energy":
+        z = 0.01 * torch.randn(N, D, generator=g)
+        z[torch.arange(N), torch.randint(0, D, (N,), generator=g)] = 8.0
+    elif kind == "leaky_relu":
+        z = torch.nn.functional.leaky_relu(4.0 * torch.randn(N, D, generator=g), 0.2) * 2 ** 0.5
+        z = z * (torch.rand(N, D, generator=g) < 0.1)            # 10 % of the channels carry the energy
+    else:
+        keep = torch.rand(K, D, generator=g) < 0.03
+        cb = cb * keep * 6.0
+        z = cb[torch.randint(0, K, (N,), generator=g)] + 0.05 * torch.randn(N, D, generator=g)
+    z = z.contiguous()
+    lay = ops.layout_of(z.shape, D, 1)
+    pcb = ops.prepare_codebook(cb.to(DEV))
+    idx = ops.search(z.to(DEV), lay, pcb, mode="tensor")
+    par = vq_oracle.classify_indices(idx, z, cb)
+    assert par.mismatch == 0, par
+    exact = ops.search(z.to(DEV), lay, pcb, mode="exact")
+    par2 = vq_oracle.classify_indices(exact, z, cb)
+    assert par2.mismatch == 0, par2
+
+
+def test_non_finite_latents_give_in_range_indices():
+    """Rows containing NaN / Inf: torch.argmin still returns an index in [0, K); so must we."""
+    z, cb = vq_oracle.synth((256, 64), 128, 64, "T", seed=3)
+    z[5, 3] = float("nan")
+    z[17, :] = float("inf")
+    z[40, 0] = float("-inf")
+    for mode in ("tensor", "exact"):
+        vq = VectorQuantizer(128, 64, 0.25, search_mode=mode).to(DEV).eval()
+        with torch.no_grad():
+            vq.embedding.weight.copy_(cb.to(DEV))
+            _, _, (_, _, idx) = vq(z.to(DEV))
+            enc = vq.encode_indices(z.to(DEV))
+        for t in (idx.view(-1), enc):
+            assert int(t.min()) >= 0 and int(t.max()) < 128, mode
+        ok = torch.ones(256, dtype=torch.bool)
+        ok[[5, 17, 40]] = False
+        ref = vq_oracle.nearest(z[ok], cb)
+        assert torch.equal(idx.view(-1).cpu()[ok], ref), mode
+
+
+# ------------------------------------------------------------------------------------------------
+# property tests
+# ------------------------------------------------------------------------------------------------
+_dims = st.sampled_from([1, 4, 64, 256, 512])
+_fast = settings(max_examples=20, deadline=None, derandomize=True,
+                 suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+
+
+def _search_all_modes(z, cb):
+    D = cb.shape[1]
+    lay = ops.layout_of(z.shape, D, 1)
+    pcb = ops.prepare_codebook(cb.to(DEV))
+    out = {"exact": ops.search(z.to(DEV), lay, pcb, mode="exact").cpu()}
+    if ops.tensor_path_supported(cb.shape[0], D):
+        out["tensor"] = ops.search(z.to(DEV), lay, pcb, mode="tensor").cpu()
+    return out
+
+
+@_fast
+@given(D=_dims, K=st.integers(1, 700), N=st.integers(1, 900), seed=st.integers(0, 2 ** 16), dist=st.sampled_from("TI"))
+def test_property_ragged_shapes_match_oracle(D, K, N, seed, dist):
+    """Any N, K (ragged, tiny, K = 1) and every supported D: same indices as the oracle."""
+    z, cb = vq_oracle.synth((N, D), K, D, dist, seed=seed)
+    for mode, idx in _search_all_modes(z, cb).items():
+        par = vq_oracle.classify_indices(idx, z, cb)
+        assert par.mismatch == 0, (mode, par)
+        if dist == "T" and D >= 64:
+            assert par.near_tie == 0, (mode, par)
+
+
+@_fast
+@given(D=st.sampled_from([4, 64, 256]), K=st.integers(2, 300), seed=st.integers(0, 2 ** 16), ndup=st.integers(1, 6))
+def test_property_duplicate_rows_take_the_lowest_index(D, K, seed, ndup):
+    """quantize.py:50 (torch.argmin) returns the first occurrence: latents equal to a duplicated code resolve to the
+    lowest index among the copies, on both search paths."""
+    g = torch.Generator().manual_seed(seed)
+    z, cb = vq_oracle.synth((256, D), K, D, "T", seed=seed)
+    src = torch.randint(0, K, (ndup,), generator=g)
+    dst = torch.randint(0, K, (ndup,), generator=g)
+    cb[dst] = cb[src]                                    # dst rows become copies of src rows
+    z[:ndup] = cb[src]                                   # latents sitting exactly on duplicated codes
+    ref = vq_oracle.nearest(z, cb)
+    for mode, idx in _search_all_modes(z, cb).items():
+        par = vq_oracle.classify_indices(idx, z, cb)
+        assert par.mismatch == 0, (mode, par)
+        # exact ties: the lowest index among identical rows
+        for n in range(ndup):
+            same = (cb == cb[ref[n]]).all(1).nonzero().view(-1)
+            assert int(idx[n]) == int(same.min()) == int(ref[n]), (mode, n)
+
+
+@_fast
+@given(D=st.sampled_from([4, 64, 256]), K=st.integers(2, 400), seed=st.integers(0, 2 ** 16))
+def test_property_codebook_permutation_equivariance(D, K, seed):
+    """Permuting the codebook rows permutes the answer: perm[idx'] == idx (distribution T: no ties)."""
+    z, cb = vq_oracle.synth((300, D), K, D, "T", seed=seed)
+    perm = torch.randperm(K, generator=torch.Generator().manual_seed(seed + 1))
+    a = _search_all_modes(z, cb)
+    b = _search_all_modes(z, cb[perm].contiguous())
+    for mode in a:
+        assert torch.equal(perm[b[mode]], a[mode]), mode
+
+
+@_fast
+@given(D=st.sampled_from([4, 64, 256]), K=st.integers(2, 400), seed=st.integers(0, 2 ** 16), e=st.integers(-12, 12))
+def test_property_power_of_two_scale_invariance(D, K, seed, e):
+    """Scaling latents AND codebook by 2^e is exact in FP32: indices are unchanged, z_q scales by 2^e bit for bit and
+    the loss by 4^e."""
+    z, cb = vq_oracle.synth((4, D, 4, 8) if D >= 4 else (128, D), K, D, "T", seed=seed)
+    s = 2.0 ** e
+    outs = []
+    for zz, cc in ((z, cb), (z * s, cb * s)):
+        vq = VectorQuantizer(K, D, 0.25).to(DEV).eval()
+        with torch.no_grad():
+            vq.embedding.weight.copy_(cc.to(DEV))
+            z_q, loss, (_, _, idx) = vq(zz.to(DEV))
+        outs.append((z_q.cpu(), float(loss), idx.view(-1).cpu()))
+    assert torch.equal(outs[0][2], outs[1][2])
+    assert torch.equal(outs[0][0] * s, outs[1][0])
+    assert abs(outs[1][1] - outs[0][1] * s * s) <= 1e-6 * abs(outs[1][1])
+
+
+@_fast
+@given(D=st.sampled_from([4, 64, 256]), K=st.integers(1, 300), g=st.integers(1, 5), hw=st.sampled_from([(1, 1), (2, 3), (4, 4), (5, 7), (8, 8)]),
+       seed=st.integers(0, 2 ** 16))
+def test_property_forward_matches_oracle(D, K, g, hw, seed):
+    """Whole forward through the module on ragged NCHW shapes: z_q bit-exact, loss / perplexity within 1e-5."""
+    shape = (g, D, hw[0], hw[1])
+    z, cb = vq_oracle.synth(shape, K, D, "T", seed=seed)
+    vq = VectorQuantizer(K, D, 0.25).to(DEV).eval()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+        z_q, loss, (perp, onehot, idx) = vq(z.to(DEV))
+    res = vq_oracle.forward(z, cb, 0.25)
+    rows = vq_oracle.to_channel_last(z).reshape(-1, D)
+    par = vq_oracle.classify_indices(idx, rows, cb)
+    assert par.mismatch == 0, par
+    if par.exact == par.n:
+        assert torch.equal(z_q.cpu(), res.z_q)
+        torch.testing.assert_close(loss.cpu(), res.loss, rtol=1e-5, atol=1e-12)
+        torch.testing.assert_close(perp.cpu(), res.perplexity, rtol=1e-5, atol=0)
+        assert torch.equal(onehot.sum(0).cpu(), res.one_hot.sum(0))      # an unmodified caller's use of min_encodings

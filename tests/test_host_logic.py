@@ -175,3 +175,47 @@ def test_ema_statistics_one_all_reduce_gloo():
     idx = vq_oracle.nearest(rows, cb)
     assert counts.dtype == torch.int32 and torch.equal(counts.long(), torch.bincount(idx, minlength=K))
     torch.testing.assert_close(resid, torch.zeros(K, D).index_add_(0, idx, rows - cb[idx]), rtol=1e-5, atol=1e-5)
+
+
+def _ema_split_worker(rank, world, port, q):
+    """start_reduce_ema_stats / finish_reduce_ema_stats (the deferred form used to hide the all-reduce under the
+    backward) give the same sums as the one-shot form, and an empty shard joins with zero statistics."""
+    import torch.distributed as dist
+    from ccvs_b200 import dist as vqd
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    K, D = 6, 4
+    buf, resid_view = vqd.ema_stats_buffer(K, D, "cpu")
+    g = torch.Generator().manual_seed(100 + rank)
+    if rank == 0:
+        resid_view.copy_(torch.randn(K, D, generator=g))
+        counts = torch.randint(0, 5, (K,), generator=g, dtype=torch.int32)
+    else:                      # empty shard: all-zero packed buffer
+        buf.zero_()
+        counts = torch.zeros(K, dtype=torch.int32)
+    mine = (resid_view.clone(), counts.clone())
+    work = vqd.start_reduce_ema_stats(buf, counts, K, D)
+    resid, cnt = vqd.finish_reduce_ema_stats(work, buf, K, D)
+    q.put((rank, mine[0], mine[1], resid.clone(), cnt.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_deferred_ema_statistics_gloo():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ema_split_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got.sort(key=lambda t: t[0])
+    want_resid = got[0][1] + got[1][1]
+    want_counts = got[0][2] + got[1][2]
+    for _, _, _, resid, cnt in got:
+        assert torch.equal(resid, want_resid) and torch.equal(cnt, want_counts)
+    assert torch.equal(got[1][1], torch.zeros(6, 4))
