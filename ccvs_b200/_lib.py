@@ -83,6 +83,7 @@ SIGNATURES = {
     "ccvsq_gather": (c_int, [_P, _P, c_int, Layout, _P, _P, _P]),
     "ccvsq_backward_dz": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, _P, _P]),
     "ccvsq_code_stats": (c_int, [_P, Layout, _P, c_int, _P, c_float, _P, _P, _P]),
+    "ccvsq_code_stats_fixed": (c_int, [_P, Layout, _P, c_int, _P, c_float, _P, _P, _P, _P, _P]),
     "ccvsq_finalize": (c_int, [_P, _P, _P, _P, c_int, c_int, c_double, c_double, c_float, _P, _P, _P, _P]),
     "ccvsq_ema_update": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
     "ccvsq_gather_add": (c_int, [_P, _P, c_int, c_int, c_int64, _P, c_int64, _P, _P, _P]),

@@ -68,7 +68,7 @@ extern "C" int ccvsq_quantize_forward(const ccvsq_forward_args* a, void* stream)
                 (unsigned long long)a->workspace_bytes, (unsigned long long)(p.total + 256));
 
   // header: [0] queue count | [1,2] fallback counters | [3] ticket | [4,5] fp64 sum of squared errors |
-  //         [6] max ||e|| (when the side data is built here) | [16, 16+K) per-code counts
+  //         [6] max ||e||, [7] max ||e - bf16(e)|| (when the side data is built here) | [16, 16+K) per-code counts
   int32_t* hdr = a->header;
   CCVSQ_CUDA(cudaMemsetAsync(hdr, 0, (size_t)(CCVSQ_HEADER_INTS + K) * sizeof(int32_t), st));
   // (all memsets come first: the kernels below form one programmatic-dependent-launch chain)
@@ -88,7 +88,7 @@ extern "C" int ccvsq_quantize_forward(const ccvsq_forward_args* a, void* stream)
     e_max = tensor ? reinterpret_cast<float*>(hdr + 6) : nullptr;
   }
   if (own_cb || a->prepare) {
-    if (e_max && !own_cb) CCVSQ_CUDA(cudaMemsetAsync(e_max, 0, sizeof(float), st));
+    if (e_max && !own_cb) CCVSQ_CUDA(cudaMemsetAsync(e_max, 0, 2 * sizeof(float), st));
     if (int rc = prepare_codebook_launch(a->E, K, D, e_sq, e_bf16, e_max, st)) return rc;
   }
 

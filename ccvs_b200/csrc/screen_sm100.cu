@@ -167,6 +167,32 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32
         : "memory");
   }
 }
+// D[tmem] (+)= A[smem] * B[smem]^T (SS form): used for the one bias step of the wide-tile plan, whose constant A block
+// lives in shared memory because 2 x 128 accumulator columns + 2 A buffers fill all 512 tensor-memory columns
+template <int CG>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_desc_lo, uint32_t a_desc_hi, uint32_t b_desc_lo,
+                                        uint32_t b_desc_hi, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 ad, {%1, %2};\n\tmov.b64 bd, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_desc_lo), "r"(a_desc_hi), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 ad, {%1, %2};\n\tmov.b64 bd, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_desc_lo), "r"(a_desc_hi), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// barrier among `nthreads` threads (a multiple of 32) on hardware barrier `id` (1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// register re-balancing between warpgroups (4 consecutive warps execute it together)
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -257,10 +283,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // kernel configuration
 // ------------------------------------------------------------------------------------------------
 constexpr int BM = 128;              // latent rows per CTA (TMEM lanes)
-// codes per accumulator tile (UMMA N) is a template parameter: 96 (long sweeps: fewest per-tile hand-offs)
-// or 64 (three accumulators AND two A buffers fit the 512 tensor-memory columns up to D = 256, and three
-// accumulators fit beside a D = 512 A buffer)
-constexpr int LCAP = 16;             // candidate-list entries (groups of 4 codes) per row
+// Codes per accumulator tile (UMMA N) is a template parameter:
+//   128  wide-tile plan (short code sweeps, the BASELINE K = 1024 shapes): next to concurrent tensor-memory readers a
+//        128-column MMA stream keeps 87 % of its rate where a 64-column one keeps 59 % (the per-instruction arbitration
+//        loss is the same, the instruction twice as long: profiles/r01_tmem_mma_microbench.txt).  2 accumulators +
+//        2 A buffers fill the 512 columns exactly, so the constant bias operand moves to shared memory (one SS-form
+//        MMA per tile), and TWO epilogue warpgroups split the columns of every tile (64 each): the accumulator is
+//        handed back as soon as both have issued their loads, and each has two tile times for its max trees / lists.
+//   96   long sweeps (K >= 2304): three accumulators, one A buffer
+//   64   D = 512 / fallback plans
+constexpr int LCAP = 16;             // candidate-list entries (groups of 4 codes) per row and epilogue group
 constexpr int LKEEP = LCAP - 8;      // one slow path appends up to 8 groups: compact down to this many first
 // candidate list in shared memory: entry e of a row = 4 raw scores at sc_base + e*ENT_STRIDE (sc_base = list +
 // row*16) and the first code of the group at co_base + e*ENT_STRIDE (co_base = list + BM*16 + row*4): ONE stride
@@ -270,33 +302,48 @@ constexpr uint32_t SC_STRIDE = ENT_STRIDE;
 constexpr uint32_t CO_STRIDE = ENT_STRIDE;
 constexpr uint32_t CO_OFFSET = BM * 16;
 constexpr uint32_t LIST_BYTES = LCAP * ENT_STRIDE;
-constexpr int SCREEN_THREADS = 512;
 constexpr int MAX_SLOTS = 16;
-// tensor-memory columns (32-bit): two accumulators, the constant bias-extension A block, A buffers
-//   [0, nacc*BN) accumulators | [nacc*BN, +8) bias-extension A block | then abuf_n A buffers of D/2
+// tensor-memory columns (32-bit):
+//   BN < 128 : [0, nacc*BN) accumulators | [nacc*BN, +8) bias-extension A block | then abuf_n A buffers of D/2
+//   BN = 128 : [0, 2*128) accumulators | abuf_n A buffers of D/2 (the bias-extension A block is in shared memory)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_ACC = 8;
 
+template <int BN>
+struct ScreenCfg {
+  static constexpr bool WIDE = BN == 128;
+  static constexpr int NEPG = WIDE ? 2 : 1;              // epilogue warpgroups
+  static constexpr int EP_WARP0 = 4;                     // warps 0-3: TMA, MMA, allocator, L2 prefetcher
+  static constexpr int LD_WARP0 = EP_WARP0 + 4 * NEPG;   // 8 loader warps follow the epilogue warps
+  static constexpr int THREADS = (LD_WARP0 + 8) * 32;    // 512 / 640
+};
+__host__ __device__ constexpr int screen_threads(int bn) { return bn == 128 ? 640 : 512; }
+
 struct ScreenSmem {
-  uint32_t slots, list, norm, drop, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
+  uint32_t slots, list, norm, drop, epst, cblk, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
   uint32_t block_bytes, ext_off, slot_bytes, slot_tx;
   int nslots;
 };
 __host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg, int bn) {
   ScreenSmem s;
+  const uint32_t nepg = bn == 128 ? 2 : 1;
   const uint32_t rows = bn / cg;                    // codes of a tile held by one CTA
   s.block_bytes = rows * 128;                       // one 64-dim block, 128B-swizzled
   s.ext_off = dblk * s.block_bytes;                 // bias extension: [2 K-chunks][rows][16 B]
   s.slot_tx = s.ext_off + rows * 32;
   s.slot_bytes = (s.slot_tx + 1023u) & ~1023u;
-  const uint32_t fixed = LIST_BYTES + 2 * 2 * BM * 4 + BM * 4 + 512;
+  const uint32_t norm_bytes = 2 * 2 * 2 * BM * 4;   // [A buffer][loader half][||z||^2, ||z - bf16(z)||^2][row]
+  const uint32_t cblk_bytes = bn == 128 ? BM * 32 : 0;
+  const uint32_t fixed = nepg * LIST_BYTES + norm_bytes + nepg * BM * 4 + nepg * BM * 8 + cblk_bytes + 512;
   int n = (int)((227u * 1024u - fixed) / s.slot_bytes);
   s.nslots = n > MAX_SLOTS ? MAX_SLOTS : n;
   uint32_t off = 0;
   s.slots = off; off += (uint32_t)s.nslots * s.slot_bytes;
-  s.list = off;  off += LIST_BYTES;                 // { [entry][row] float4 | [entry][row] u32 }
-  s.norm = off;  off += 2 * 2 * BM * 4;             // [A buffer][loader half][row] partial ||z||^2
-  s.drop = off;  off += BM * 4;                     // [row] best score dropped from an overflowing list
+  s.list = off;  off += nepg * LIST_BYTES;          // per epilogue group { [entry][row] float4 | [entry][row] u32 }
+  s.norm = off;  off += norm_bytes;
+  s.drop = off;  off += nepg * BM * 4;              // [group][row] best score dropped from an overflowing list
+  s.epst = off;  off += nepg * BM * 8;              // [group][row] {entries, running max} published at the end of a sweep
+  s.cblk = off;  off += cblk_bytes;                 // constant A block (1,1,1,0,...) of the bias step: [2 K-chunks][128 rows][16 B]
   s.bars = off;  off += 512;
   s.total = off;
   return s;
@@ -369,32 +416,42 @@ struct ScreenOut {
 };
 constexpr int TRACE_SWEEPS = 32;
 
+// the candidate lists of one row: one per epilogue group (the wide-tile plan keeps two, each over half the columns)
+struct RowLists {
+  uint32_t sc[2], co[2], n[2], drop[2];
+};
+
 // Candidates of one row once all codes have been seen: every listed code with score >= runmax -
-// margin, sorted by (score desc, code asc), at most n_cand of them.  The list is in increasing code
-// order, so a strict '>' scan keeps the lowest code among equal scores.  Rows with exactly one
+// margin, sorted by (score desc, code asc), at most n_cand of them.  Rows with exactly one
 // candidate are final; the others are queued for FP32 re-scoring.  Kept out of line (and rolled) so
 // the per-tile loop stays small in the instruction cache.
-__device__ __noinline__ void finalize_row(uint32_t sc_base, uint32_t co_base, uint32_t n, float runmax,
-                                          float margin, uint32_t drop_addr, int n_cand, int64_t row,
+template <int NL>
+__device__ __noinline__ void finalize_row(const RowLists L2, float runmax, float margin, int n_cand, int64_t row,
                                           const ScreenOut out) {
   const float thr = runmax - margin;
-  float dropped_max;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dropped_max) : "r"(drop_addr));
+  float dropped_max = -FLT_MAX;
   uint32_t within = 0;
   float best_s = -INFINITY;
   int best_i = -1;
-#pragma unroll 1
-  for (uint32_t e = 0; e < n; ++e) {
-    float sc[4];
-    uint32_t code;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {      // branch-free (padding codes carry -3e38 and never pass)
-      within += (sc[u] >= thr) ? 1u : 0u;
-      const bool better = sc[u] > best_s;
-      best_s = better ? sc[u] : best_s;
-      best_i = better ? (int)code + u : best_i;
+  for (int l = 0; l < NL; ++l) {             // (unrolled: the struct stays in registers)
+    float dm;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dm) : "r"(L2.drop[l]));
+    dropped_max = fmaxf(dropped_max, dm);
+#pragma unroll 1
+    for (uint32_t e = 0; e < L2.n[l]; ++e) {
+      float sc[4];
+      uint32_t code;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(L2.sc[l] + e * SC_STRIDE));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(L2.co[l] + e * CO_STRIDE));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {      // branch-free (padding codes carry -3e38 and never pass)
+        within += (sc[u] >= thr) ? 1u : 0u;
+        const int i = (int)code + u;
+        const bool better = sc[u] > best_s || (sc[u] == best_s && i < best_i);   // lowest code among equal scores
+        best_s = better ? sc[u] : best_s;
+        best_i = better ? i : best_i;
+      }
     }
   }
   const uint8_t flag = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped_max >= thr ? 2 : 0));
@@ -420,19 +477,22 @@ __device__ __noinline__ void finalize_row(uint32_t sc_base, uint32_t co_base, ui
     float bs_ = -INFINITY;
     int bi = 0x7fffffff;
     if (prev_i != 0x7fffffff) {
-#pragma unroll 1
-      for (uint32_t e = 0; e < n; ++e) {
-        float sc[4];
-        uint32_t code;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = (int)code + u;
-          const float x = sc[u];
-          const bool after_prev = (x < prev_s) || (x == prev_s && i > prev_i);
-          const bool better = (x > bs_) || (x == bs_ && i < bi);
-          if (x >= thr && after_prev && better) { bs_ = x; bi = i; }
+      for (int l = 0; l < NL; ++l) {
+#pragma unroll 1
+        for (uint32_t e = 0; e < L2.n[l]; ++e) {
+          float sc[4];
+          uint32_t code;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(L2.sc[l] + e * SC_STRIDE));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(L2.co[l] + e * CO_STRIDE));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = (int)code + u;
+            const float x = sc[u];
+            const bool after_prev = (x < prev_s) || (x == prev_s && i > prev_i);
+            const bool better = (x > bs_) || (x == bs_ && i < bi);
+            if (x >= thr && after_prev && better) { bs_ = x; bi = i; }
+          }
         }
       }
     }
@@ -467,6 +527,22 @@ __device__ __forceinline__ void load_chunk(float (&v)[32], const float* __restri
   }
 }
 
+// 32 FP32 values -> 16 packed BF16 pairs (RN), accumulating ||v||^2 and the squared rounding error ||v - bf16(v)||^2
+__device__ __forceinline__ void pack_chunk(const float (&v)[32], uint32_t (&pk)[16], float& ss, float& dd) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float a = v[2 * i], b = v[2 * i + 1];
+    ss = fmaf(a, a, ss);
+    ss = fmaf(b, b, ss);
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);                           // .x (low half) = even k
+    const uint32_t bits = *reinterpret_cast<uint32_t*>(&t);
+    pk[i] = bits;
+    const float da = a - __uint_as_float(bits << 16), db = b - __uint_as_float(bits & 0xffff0000u);
+    dd = fmaf(da, da, dd);
+    dd = fmaf(db, db, dd);
+  }
+}
+
 // per-tile stamps of ONE sweep (the fourth) for the DBG kernel: trace[cta][16 + tile][slot]
 #define CCVSQ_TILE_STAMP(TL, J, SLOT)                                                                              \
   do {                                                                                                             \
@@ -477,11 +553,14 @@ __device__ __forceinline__ void load_chunk(float (&v)[32], const float* __restri
   } while (0)
 
 template <int CG, bool DBG, int BN>
-__global__ void __launch_bounds__(SCREEN_THREADS, 1)
+__global__ void __launch_bounds__(screen_threads(BN), 1)
 screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_ext,
-              const float* __restrict__ z, const Lay L, const float* __restrict__ e_max, float margin_scale,
+              const float* __restrict__ z, const Lay L, const float* __restrict__ e_max, float tau,
               int K_pad, int n_tiles, int dblk, int nacc, int abuf_n, int n_cand, int num_group_tiles,
               const ScreenOut out) {
+  using Cfg = ScreenCfg<BN>;
+  constexpr bool WIDE = Cfg::WIDE;
+  constexpr int NEPG = Cfg::NEPG;
   extern __shared__ __align__(1024) uint8_t smem[];
   const ScreenSmem lay = screen_smem_layout(dblk, CG, BN);
   const uint32_t smem_base = smem_u32(smem);
@@ -490,7 +569,8 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
   const uint32_t rank = (CG == 1) ? 0u : cluster_ctarank();
   const int group = (int)blockIdx.x / CG, num_groups = (int)gridDim.x / CG;
   const int nslots = lay.nslots;
-  const uint32_t TM_EXT = (uint32_t)nacc * BN, TM_A = TM_EXT + 8;   // tensor-memory column map
+  // tensor-memory column map
+  const uint32_t TM_EXT = (uint32_t)nacc * BN, TM_A = WIDE ? TM_EXT : TM_EXT + 8;
   const uint32_t a_cols = (uint32_t)dblk * 32;      // 32-bit columns per A buffer (D/2)
   constexpr int ROWS = BN / CG;                     // codes of a tile in this CTA's shared memory
 
@@ -505,7 +585,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
   auto norm_full = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 2 * MAX_ACC + 4 + b); };
   auto norm_empty = [&](int b) { return bar0 + 8u * (2 * MAX_SLOTS + 2 * MAX_ACC + 6 + b); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + lay.bars + 8u * (2 * MAX_SLOTS + 2 * MAX_ACC + 8));
-  float* norm_s = reinterpret_cast<float*>(smem + lay.norm);
+  float* norm_s = reinterpret_cast<float*>(smem + lay.norm);      // [(ab*2 + h)*2 + {0: ||z||^2, 1: ||dz||^2}][row]
 
   if ((smem_base & 1023u) != 0) __trap();   // SWIZZLE_128B needs 1024-byte aligned tiles
 
@@ -517,27 +597,39 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < MAX_ACC; ++b) {
       mbar_init(tmem_full(b), 1);
-      mbar_init(tmem_empty(b), 4 * CG);     // one arrive per epilogue warp of every CTA in the group
+      mbar_init(tmem_empty(b), 4 * NEPG * CG);   // one arrive per epilogue warp of every CTA in the group
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(a_full(b), 8 * CG);         // one arrive per loader warp of every CTA in the group
       mbar_init(a_empty(b), 1);
       mbar_init(norm_full(b), 8);
-      mbar_init(norm_empty(b), 4);
+      mbar_init(norm_empty(b), 4 * NEPG);
     }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<CG>(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  if constexpr (WIDE) {
+    // constant A block of the bias step in shared memory, K-major without swizzle: chunk kc (8 BF16 = 16 B) of row r
+    // at kc*2048 + r*16; row = (1, 1, 1, 0, ..., 0)
+    if (warp == 3) {
+      uint4* cb4 = reinterpret_cast<uint4*>(smem + lay.cblk);
+      for (int i = lane; i < 2 * BM; i += 32)
+        cb4[i] = i < BM ? make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's reads
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  if (warp >= 4 && warp < 8) {
-    // constant A block of the bias extension: (1, 1, 1, 0, ..., 0) in BF16, 16 K-elements = 8 columns
-    uint32_t ext[8] = {0x3F803F80u, 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u};
-    tmem_st8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TM_EXT, ext);
-    tmem_st_wait();
-    tc_fence_before();
+  if constexpr (!WIDE) {
+    if (warp >= 4 && warp < 8) {
+      // constant A block of the bias extension: (1, 1, 1, 0, ..., 0) in BF16, 16 K-elements = 8 columns
+      uint32_t ext[8] = {0x3F803F80u, 0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tmem_st8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TM_EXT, ext);
+      tmem_st_wait();
+      tc_fence_before();
+    }
   }
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -547,7 +639,11 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
   // (epilogue) or consume them through barriers (MMA) wait first; the others wait before they exit, so that this
   // grid's completion still implies the predecessor's.
   pdl_launch_dependents();
-  if (!out.z_stable || warp < 3 || (warp >= 4 && warp < 8)) pdl_wait();
+  if (!out.z_stable || warp < 3 || (warp >= Cfg::EP_WARP0 && warp < Cfg::LD_WARP0)) pdl_wait();
+
+  // (WIDE: 640 threads at 96 registers each.  setmaxnreg re-balancing was tried and dropped: the values every role keeps
+  //  live from the common prologue do not fit a shrunken control warpgroup, and at 96 the kernel spills ~12 words outside
+  //  the per-tile loops)
 
   if (warp == 0) {
     // =========================== TMA producer (every CTA: its half of each B tile) ===============
@@ -600,7 +696,11 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
             const uint32_t d_tmem = tmem_base + b * BN;
             const uint32_t sbase = smem_base + lay.slots + (uint32_t)slot * lay.slot_bytes;
             // bias first (overwrites the accumulator), then the D/16 K steps of the dot product
-            umma_ts<CG>(d_tmem, tmem_base + TM_EXT, desc_lo(sbase + lay.ext_off, ROWS * 16), DESC_HI_NOSW, idesc, 0u);
+            if constexpr (WIDE)
+              umma_ss<CG>(d_tmem, desc_lo(smem_base + lay.cblk, BM * 16), DESC_HI_NOSW, desc_lo(sbase + lay.ext_off, ROWS * 16),
+                          DESC_HI_NOSW, idesc, 0u);
+            else
+              umma_ts<CG>(d_tmem, tmem_base + TM_EXT, desc_lo(sbase + lay.ext_off, ROWS * 16), DESC_HI_NOSW, idesc, 0u);
             uint32_t lo = desc_lo(sbase);
             uint32_t a_addr = a_tmem;
             for (int kb = 0; kb < dblk; ++kb) {
@@ -656,9 +756,9 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       }
     }
     pdl_wait();
-  } else if (warp >= 8) {
+  } else if (warp >= Cfg::LD_WARP0) {
     // =========================== A loaders: FP32 global -> BF16 -> tensor memory ================
-    const int q = warp & 3, h = (warp - 8) >> 2;
+    const int q = warp & 3, h = (warp - Cfg::LD_WARP0) >> 2;
     const int r = q * 32 + lane;
     const int half = dblk * 32;                 // dims handled by this loader half
     const int nchunk = dblk;                    // chunks of 32 dims
@@ -677,42 +777,31 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       }
       float va[32], vb[32];
       load_chunk(va, p, L.S, valid);            // in flight while waiting for the buffer
-      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 8 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 3] = clock64(); }
+      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == Cfg::LD_WARP0 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 3] = clock64(); }
       mbar_wait_sleep(a_empty(ab), a_phase ^ 1);
-      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 8 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 4] = clock64(); }
+      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == Cfg::LD_WARP0 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 4] = clock64(); }
       tc_fence_after();
-      float ss = 0.f;
+      float ss = 0.f, dd = 0.f;                 // ||z||^2 and ||z - bf16(z)||^2 of this half row (screening margin)
       const uint32_t dst = lane_base + ab * a_cols;
       for (int c = 0; c < nchunk; c += 2) {
         if (c + 1 < nchunk) load_chunk(vb, p + (int64_t)(c + 1) * 32 * L.S, L.S, valid);
         {
           uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            ss = fmaf(va[2 * i], va[2 * i], ss);
-            ss = fmaf(va[2 * i + 1], va[2 * i + 1], ss);
-            __nv_bfloat162 t = __floats2bfloat162_rn(va[2 * i], va[2 * i + 1]);   // .x (low half) = even k
-            pk[i] = *reinterpret_cast<uint32_t*>(&t);
-          }
+          pack_chunk(va, pk, ss, dd);
           tmem_st16(dst + c * 16, pk);
         }
         if (c + 1 < nchunk) {
           if (c + 2 < nchunk) load_chunk(va, p + (int64_t)(c + 2) * 32 * L.S, L.S, valid);
           uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            ss = fmaf(vb[2 * i], vb[2 * i], ss);
-            ss = fmaf(vb[2 * i + 1], vb[2 * i + 1], ss);
-            __nv_bfloat162 t = __floats2bfloat162_rn(vb[2 * i], vb[2 * i + 1]);
-            pk[i] = *reinterpret_cast<uint32_t*>(&t);
-          }
+          pack_chunk(vb, pk, ss, dd);
           tmem_st16(dst + (c + 1) * 16, pk);
         }
       }
       tmem_st_wait();
-      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 8 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 5] = clock64(); }
+      if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == Cfg::LD_WARP0 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 5] = clock64(); }
       mbar_wait_sleep(norm_empty(ab), a_phase ^ 1);   // the epilogue has read the previous norms of this buffer
-      norm_s[(ab * 2 + h) * BM + r] = ss;
+      norm_s[((ab * 2 + h) * 2 + 0) * BM + r] = ss;
+      norm_s[((ab * 2 + h) * 2 + 1) * BM + r] = dd;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -721,15 +810,18 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       }
     }
     pdl_wait();
-  } else if (warp >= 4) {
-    // =========================== epilogue: one latent row per thread, all codes =================
-    const int q = warp & 3;
+  } else if (warp >= Cfg::EP_WARP0) {
+    // =========================== epilogue: one latent row per thread and group ===================
+    // NEPG == 1: the thread sees all codes of its row.  NEPG == 2 (wide tiles): group g sees columns [64g, 64g + 64)
+    // of every tile and keeps its own running maximum / candidate list; the two lists meet in finalize_row.
+    const int q = warp & 3, g = (warp - Cfg::EP_WARP0) >> 2;
     const int row_in_tile = q * 32 + lane;
-    const uint32_t sc_base = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
-    const uint32_t co_base = smem_base + lay.list + CO_OFFSET + (uint32_t)row_in_tile * 4u;
-    const uint32_t drop_addr = smem_base + lay.drop + (uint32_t)row_in_tile * 4u;
+    const uint32_t sc_base = smem_base + lay.list + (uint32_t)g * LIST_BYTES + (uint32_t)row_in_tile * 16u;
+    const uint32_t co_base = sc_base - (uint32_t)row_in_tile * 16u + CO_OFFSET + (uint32_t)row_in_tile * 4u;
+    const uint32_t drop_addr = smem_base + lay.drop + (uint32_t)(g * BM + row_in_tile) * 4u;
     const uint32_t te_bar = (CG == 1) ? tmem_empty(0) : mapa(tmem_empty(0), 0);
     const float emax = e_max ? __ldg(e_max) : 1.f;
+    const float demax = e_max ? __ldg(e_max + 1) : 0.00390625f;
     uint32_t tl = 0, b = 0, b_phase = 0;
 
     for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
@@ -737,7 +829,14 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       const int64_t row = ((int64_t)gt * CG + rank) * BM + row_in_tile;
       mbar_wait(norm_full(ab), a_phase);
       if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 4 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 6] = clock64(); }
-      const float margin = margin_scale * emax * sqrtf(norm_s[(ab * 2) * BM + row_in_tile] + norm_s[(ab * 2 + 1) * BM + row_in_tile]);
+      // proven margin: 2 (||dz|| max||e|| (1 + 2^-8) + ||z|| max||de||) bounds the error of the DIFFERENCE of two
+      // BF16-operand scores; 2^-13 ||z|| max||e|| covers the FP32 accumulation (see ccvsq_screen in ccvsq.h)
+      float margin;
+      {
+        const float zn = sqrtf(norm_s[((ab * 2 + 0) * 2 + 0) * BM + row_in_tile] + norm_s[((ab * 2 + 1) * 2 + 0) * BM + row_in_tile]);
+        const float dn = sqrtf(norm_s[((ab * 2 + 0) * 2 + 1) * BM + row_in_tile] + norm_s[((ab * 2 + 1) * 2 + 1) * BM + row_in_tile]);
+        margin = tau * 2.f * (dn * emax * 1.00390625f + zn * demax) + 0.0001220703125f * zn * emax;
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(norm_empty(ab));
       float runmax = -FLT_MAX;
@@ -748,8 +847,8 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         mbar_wait(tmem_full(b), b_phase);
         if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 3);
         tc_fence_after();
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
-        const int col0 = j * BN;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + (WIDE ? (uint32_t)g * 64u : 0u);
+        const int col0 = j * BN + (WIDE ? g * 64 : 0);
 
         // One 32-column chunk of this thread's row.  Fast path: maxima of the 8 groups of 4 columns (16
         // ops) and their maximum (4 ops).  A chunk can only contribute candidates if its maximum reaches
@@ -767,10 +866,10 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
               for (int i = 0; i < 32; ++i) out.dbg_scores[row * K_pad + col0 + cbase + i] = v[i];
             }
           }
-          float g[8];
+          float gm[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = fmaxf(fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), v[4 * i + 2]), v[4 * i + 3]);
-          const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), g[2]), fmaxf(fmaxf(fmaxf(g[3], g[4]), g[5]), fmaxf(g[6], g[7])));
+          for (int i = 0; i < 8; ++i) gm[i] = fmaxf(fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), v[4 * i + 2]), v[4 * i + 3]);
+          const float m = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(fmaxf(gm[3], gm[4]), gm[5]), fmaxf(gm[6], gm[7])));
           if (m >= runmax - margin) {
             // a maximum that beats the old one by more than the margin makes every listed entry stale
             if (m > runmax + margin) cnt = 0;
@@ -780,7 +879,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
             uint32_t slot[9];
             slot[0] = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) slot[i + 1] = slot[i] + (g[i] >= thr ? 1u : 0u);
+            for (int i = 0; i < 8; ++i) slot[i + 1] = slot[i] + (gm[i] >= thr ? 1u : 0u);
             const uint32_t base_sc = sc_base + cnt * ENT_STRIDE, base_co = co_base + cnt * ENT_STRIDE;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -799,32 +898,74 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           }
         };
 
-        // BN/32 chunks of 32 columns; the tcgen05.ld of the next chunk overlaps the max tree of this
-        // one, and the accumulator is handed back as soon as the last chunk is in registers
         uint32_t ra[32], rb[32];
-        tmem_ld32(taddr0, ra);
-        tmem_ld_wait();
-        tmem_ld32(taddr0 + 32, rb);
-        process(ra, 0);
-        tmem_ld_wait();
-        if constexpr (BN == 96) {
-          tmem_ld32(taddr0 + 64, ra);
-          process(rb, 32);
+        if constexpr (WIDE) {
+          // both 32-column chunks of this group's half tile at once; the accumulator goes back to the MMA warp as
+          // soon as they are in registers (the other group does the same with its half), the max trees run after
+          tmem_ld32(taddr0, ra);
+          tmem_ld32(taddr0 + 32, rb);
           tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
+          }
+          if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 4);
+          process(ra, 0);
+          process(rb, 32);
+        } else {
+          // BN/32 chunks of 32 columns; the tcgen05.ld of the next chunk overlaps the max tree of this
+          // one, and the accumulator is handed back as soon as the last chunk is in registers
+          tmem_ld32(taddr0, ra);
+          tmem_ld_wait();
+          tmem_ld32(taddr0 + 32, rb);
+          process(ra, 0);
+          tmem_ld_wait();
+          if constexpr (BN == 96) {
+            tmem_ld32(taddr0 + 64, ra);
+            process(rb, 32);
+            tmem_ld_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
+          }
+          if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 4);
+          if constexpr (BN == 96) process(ra, 64); else process(rb, 32);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
-        }
-        if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 4);
-        if constexpr (BN == 96) process(ra, 64); else process(rb, 32);
         if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 5);
         if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
       }
 
       if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 4 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 7] = clock64(); }
-      if (row < L.N) finalize_row(sc_base, co_base, cnt, runmax, margin, drop_addr, n_cand, row, out);
+      if constexpr (WIDE) {
+        // the two groups of a lane quadrant publish {entries, running max}, meet, and split the 32 rows between them
+        const uint32_t st0 = smem_base + lay.epst + (uint32_t)row_in_tile * 8u;
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st0 + (uint32_t)g * BM * 8u), "r"(cnt), "r"(__float_as_uint(runmax)) : "memory");
+        named_bar_sync(1 + q, 64);
+        if ((lane >> 4) == g && row < L.N) {
+          uint32_t n0, m0, n1, m1;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(n0), "=r"(m0) : "r"(st0));
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(n1), "=r"(m1) : "r"(st0 + BM * 8u));
+          RowLists rl;
+          const uint32_t l0 = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
+          rl.sc[0] = l0;              rl.co[0] = l0 - (uint32_t)row_in_tile * 12u + CO_OFFSET;
+          rl.sc[1] = l0 + LIST_BYTES; rl.co[1] = rl.co[0] + LIST_BYTES;
+          rl.n[0] = n0; rl.n[1] = n1;
+          rl.drop[0] = smem_base + lay.drop + (uint32_t)row_in_tile * 4u;
+          rl.drop[1] = rl.drop[0] + BM * 4u;
+          finalize_row<2>(rl, fmaxf(__uint_as_float(m0), __uint_as_float(m1)), margin, n_cand, row, out);
+        }
+        named_bar_sync(1 + q, 64);              // the partner has read this group's list: it may be reused
+      } else {
+        if (row < L.N) {
+          RowLists rl;
+          rl.sc[0] = sc_base; rl.co[0] = co_base; rl.n[0] = cnt; rl.drop[0] = drop_addr;
+          rl.sc[1] = rl.co[1] = rl.n[1] = rl.drop[1] = 0;
+          finalize_row<1>(rl, runmax, margin, n_cand, row, out);
+        }
+      }
     }
   }
 
@@ -875,9 +1016,9 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int64
 
 template <int CG, int BN>
 static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const float* e_max,
-                         float margin_scale, int K, int K_pad, int D, int n_cand, int nacc, int abuf,
+                         float tau, int K, int K_pad, int D, int n_cand, int nacc, int abuf,
                          const ScreenOut& out, cudaStream_t st) {
-  static_assert(BN == 96 || BN == 64, "epilogue is written for 2 or 3 chunks of 32 columns (narrower / odd widths were measured and dropped: profiles/r01_screen_history.md)");
+  static_assert(BN == 128 || BN == 96 || BN == 64, "epilogue is written for 2 or 3 chunks of 32 columns per group (narrower / odd widths were measured and dropped: profiles/r01_screen_history.md)");
   const int dblk = D / 64;
   const ScreenSmem lay = screen_smem_layout(dblk, CG, BN);
   CCVSQ_REQUIRE(lay.nslots >= 1, CCVSQ_UNSUPPORTED, "screen: D=%d leaves room for %d B slots", D, lay.nslots);
@@ -896,7 +1037,7 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
   const int groups = (int)(group_tiles < max_groups ? group_tiles : max_groups);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CG));
-  cfg.blockDim = dim3(SCREEN_THREADS);
+  cfg.blockDim = dim3(screen_threads(BN));
   cfg.dynamicSmemBytes = lay.total;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -911,38 +1052,49 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
   const int n_tiles = (K + BN - 1) / BN;          // rows [K, n_tiles*BN) of the shadow are padding (bias -3e38)
   CCVSQ_REQUIRE(n_tiles * BN <= K_pad, CCVSQ_BAD_SHAPE, "screen: codebook shadow has %d rows, the sweep needs %d",
                 K_pad, n_tiles * BN);
-  CCVSQ_CUDA(cudaLaunchKernelEx(&cfg, kern, mb, mx, z, L, e_max, margin_scale, K_pad, n_tiles, dblk, nacc, abuf,
+  CCVSQ_CUDA(cudaLaunchKernelEx(&cfg, kern, mb, mx, z, L, e_max, tau, K_pad, n_tiles, dblk, nacc, abuf,
                                 n_cand, (int)group_tiles, out));
   return CCVSQ_OK;
 }
 
-// Tensor-memory budget (512 columns): nacc accumulators of BN columns, 8 columns of bias extension,
-// abuf A buffers of D/2.  The MMA -> commit -> epilogue -> arrive -> MMA chain of one accumulator is longer
-// than two tile times, so three accumulators come first.  Long code sweeps then prefer the wider tile
-// (fewer hand-offs per code) over a second A buffer (one bubble per sweep); short sweeps prefer streaming
-// the next A tile under the MMAs, which at D = 256 only fits with 64-column accumulators.
+// Tensor-memory budget (512 columns).  Narrow tiles: nacc accumulators of BN columns, 8 columns of bias extension, abuf A
+// buffers of D/2; the MMA -> commit -> epilogue -> arrive -> MMA chain of one accumulator is longer than two tile
+// times, so three accumulators come first.  Wide tiles (BN = 128): two accumulators + abuf A buffers, nothing else.
+// Short code sweeps take the wide plan (see the note at `BM`); long sweeps (K >= 2304) keep 96-column tiles with three
+// accumulators and one A buffer (fewest hand-offs per code; MMA-bound at 86-90 % of the BF16 burst peak).
 struct ScreenPlan { int bn, nacc, abuf; };
-static ScreenPlan plan_screen(int K, int D) {
+static bool plan_fits(int D, int bn, int nacc, int abuf) {
   const int a_cols = D / 2;
-  auto fits = [&](int bn, int nacc, int abuf) { return nacc * bn + 8 + abuf * a_cols <= (int)TMEM_COLS; };
+  if (bn == 128) return nacc == 2 && 2 * 128 + abuf * a_cols <= (int)TMEM_COLS;
+  return nacc * bn + 8 + abuf * a_cols <= (int)TMEM_COLS;
+}
+static ScreenPlan plan_screen(int K, int D) {
+  auto fits = [&](int bn, int nacc, int abuf) { return plan_fits(D, bn, nacc, abuf); };
   static const int forced_bn = [] { const char* e = getenv("CCVSQ_SCREEN_BN"); return e ? atoi(e) : 0; }();
-  // CCVSQ_SCREEN_PLAN=bn,nacc,abuf forces a plan for short sweeps (A/B runs)
+  // CCVSQ_SCREEN_PLAN=bn,nacc,abuf forces a plan (A/B runs)
   static const ScreenPlan forced = [] {
     ScreenPlan p = {0, 0, 0};
     const char* e = getenv("CCVSQ_SCREEN_PLAN");
     if (e) sscanf(e, "%d,%d,%d", &p.bn, &p.nacc, &p.abuf);
     return p;
   }();
-  if (forced.bn && (K + 95) / 96 < 24 && (forced.bn == 64 || forced.bn == 96) && forced.nacc >= 1 && forced.nacc <= MAX_ACC &&
+  if (forced.bn && (forced.bn == 64 || forced.bn == 96 || forced.bn == 128) && forced.nacc >= 1 && forced.nacc <= MAX_ACC &&
       forced.abuf >= 1 && forced.abuf <= 2 && fits(forced.bn, forced.nacc, forced.abuf))
     return forced;
   const bool long_sweep = (K + 95) / 96 >= 24;
   ScreenPlan best = {96, 2, 1};
   const ScreenPlan order_long[] = {{96, 3, 2}, {96, 3, 1}, {64, 3, 2}, {64, 3, 1}, {96, 2, 2}, {96, 2, 1}};
-  const ScreenPlan order_short[] = {{96, 3, 2}, {64, 3, 2}, {96, 3, 1}, {64, 3, 1}, {96, 2, 2}, {96, 2, 1}};
-  for (const ScreenPlan& p : long_sweep ? order_long : order_short) {
+  const ScreenPlan order_short[] = {{128, 2, 2}, {128, 2, 1}, {96, 3, 2}, {64, 3, 2}, {96, 3, 1}, {64, 3, 1}, {96, 2, 2}, {96, 2, 1}};
+  const ScreenPlan* order = long_sweep ? order_long : order_short;
+  const int n_order = long_sweep ? 6 : 8;
+  for (int i = 0; i < n_order; ++i) {
+    const ScreenPlan& p = order[i];
     if (forced_bn && p.bn != forced_bn) continue;
     if (fits(p.bn, p.nacc, p.abuf)) { best = p; break; }
+  }
+  if (forced_bn == 128 && long_sweep) {       // A/B: wide tiles on long sweeps
+    if (fits(128, 2, 2)) best = {128, 2, 2};
+    else if (fits(128, 2, 1)) best = {128, 2, 1};
   }
   return best;
 }
@@ -966,22 +1118,24 @@ static int screen_impl(const float* z, ccvsq_layout lay, const void* E_bf16, con
                 "screen: z and the codebook shadow must be 16-byte aligned");
   CCVSQ_REQUIRE(cta_group == 1 || cta_group == 2, CCVSQ_BAD_SHAPE, "screen: cta_group=%d", cta_group);
   const int K_pad = ccvsq_codebook_rows(K);
-  const float margin_scale = margin_tau * 0.00390625f;   // tau * 2^-8
+  const float margin_scale = margin_tau;
   const ScreenPlan pl = plan_screen(K, D);
-  CCVSQ_REQUIRE(pl.nacc * pl.bn + 8 + pl.abuf * (D / 2) <= (int)TMEM_COLS, CCVSQ_UNSUPPORTED,
+  CCVSQ_REQUIRE(plan_fits(D, pl.bn, pl.nacc, pl.abuf), CCVSQ_UNSUPPORTED,
                 "screen: D=%d does not fit the tensor-memory budget", D);
   cudaStream_t st = (cudaStream_t)stream;
   if (cta_group == 2) {
+    if (pl.bn == 128) return launch_screen<2, 128>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
     if (pl.bn == 64) return launch_screen<2, 64>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
     return launch_screen<2, 96>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
   }
+  if (pl.bn == 128) return launch_screen<1, 128>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
   if (pl.bn == 64) return launch_screen<1, 64>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
   return launch_screen<1, 96>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
 }
 
-// rows of the BF16 codebook shadow: enough for a sweep with either tile width
+// rows of the BF16 codebook shadow: enough for a sweep with any tile width (128 covers 64)
 extern "C" int ccvsq_codebook_rows(int K) {
-  const int a = (K + 95) / 96 * 96, b = (K + 63) / 64 * 64;
+  const int a = (K + 95) / 96 * 96, b = (K + 127) / 128 * 128;
   return a > b ? a : b;
 }
 

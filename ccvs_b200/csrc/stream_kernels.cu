@@ -93,15 +93,23 @@ __global__ void prepare_codebook_kernel(const float* __restrict__ E, int K, int 
   float acc = 0.f;
   if (k < K) {
     const float* e = E + (size_t)k * D;
+    float dacc = 0.f;                         // ||e - bf16(e)||^2: the code's own rounding error (screening margin)
     for (int j = lane; j < D; j += 32) {
       float v = e[j];
       acc = fmaf(v, v, acc);
-      if (Eb) Eb[(size_t)k * DE + j] = __float2bfloat16_rn(v);
+      const __nv_bfloat16 r = __float2bfloat16_rn(v);
+      const float dv = v - __bfloat162float(r);
+      dacc = fmaf(dv, dv, dacc);
+      if (Eb) Eb[(size_t)k * DE + j] = r;
     }
     acc = warp_sum(acc);
+    dacc = warp_sum(dacc);
     if (lane == 0) {
       e_sq[k] = acc;
-      if (e_max_bits) atomicMax(e_max_bits, __float_as_uint(sqrtf(acc)));  // acc >= 0: uint order == float order
+      if (e_max_bits) {                       // both >= 0: uint order == float order
+        atomicMax(e_max_bits, __float_as_uint(sqrtf(acc)));
+        atomicMax(e_max_bits + 1, __float_as_uint(sqrtf(dacc)));
+      }
     }
   } else if (Eb) {
     for (int j = lane; j < D; j += 32) Eb[(size_t)k * DE + j] = __float2bfloat16_rn(0.f);
@@ -301,6 +309,74 @@ __global__ void __launch_bounds__(NT) code_stats_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Deterministic per-code sums: 64-bit fixed point.  FP32 atomics make resid / dE depend on the order in which CTAs
+// reach a code row (run-to-run differences in the last bits).  Integer addition is associative: every term
+// t = x - sub*E[k] is scaled by a power of two 2^s chosen from the data (so that N terms cannot overflow 62 bits),
+// rounded to an integer ONCE, and accumulated with 64-bit integer atomics; the sum is exact in that grid and the
+// result bit-identical for any launch order.  Resolution 2^-s = 2^(e + ceil(log2 N) - 60) with 2^e > max|t|.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ a, size_t na, const float* __restrict__ b,
+                                                     size_t nb, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(a[i]));
+  if (b)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(b[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // NaN / Inf never enter: fmaxf drops NaN, Inf is clamped to FLT_MAX by the consumer
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // m >= 0: uint order == float order
+}
+
+__device__ __forceinline__ int fixed_shift(float amax, float sub, int64_t N) {
+  int e = 0;
+  const float bound = fminf(amax, 1.0e38f) * (1.f + fabsf(sub));
+  frexpf(fmaxf(bound, 1e-37f), &e);             // bound < 2^e
+  int lg = 0;
+  while (((int64_t)1 << lg) < N) ++lg;
+  return 60 - e - lg;
+}
+
+__global__ void __launch_bounds__(NT) code_stats_fixed_kernel(const float* __restrict__ x, Lay L,
+                                                              const float* __restrict__ E, int K,
+                                                              const int64_t* __restrict__ idx, float sub,
+                                                              const float* __restrict__ amax,
+                                                              unsigned long long* __restrict__ acc,
+                                                              int32_t* __restrict__ counts) {
+  extern __shared__ float tile[];
+  const int CP = L.C + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int np = (int)min((int64_t)PT, L.P - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = np * L.mult;
+  const int64_t n0 = p0 * L.mult;
+  const int sh = fixed_shift(__ldg(amax), sub, L.N);
+  tile_load(x, L, p0, np, tile);
+  __syncthreads();
+  for (int r = warp; r < rows; r += NW) {
+    const int64_t n = n0 + r;
+    int64_t k = idx[n];
+    if (k < 0 || k >= K) continue;
+    const int p = r / L.mult, m = r - p * L.mult;
+    const float* t = tile + p * CP + m * L.D;
+    unsigned long long* dst = acc + (size_t)k * L.D;
+    const float* e = (sub != 0.f) ? E + (size_t)k * L.D : nullptr;
+    for (int j = lane; j < L.D; j += 32) {
+      const float v = e ? __fsub_rn(t[j], __fmul_rn(sub, __ldg(e + j))) : t[j];
+      const long long q = __float2ll_rn(ldexpf(v, sh));
+      atomicAdd(dst + j, (unsigned long long)q);
+    }
+    if (counts && lane == 0) atomicAdd(counts + k, 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) fixed_to_float_kernel(const long long* __restrict__ acc, size_t n, float sub, int64_t N,
+                                                             const float* __restrict__ amax, float* __restrict__ out) {
+  const int sh = fixed_shift(__ldg(amax), sub, N);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (float)ldexp((double)acc[i], -sh);
+}
+
+// ------------------------------------------------------------------------------------------------
 // decode gather, row-major output: one warp per row, 128-bit loads/stores when D % 4 == 0
 // ------------------------------------------------------------------------------------------------
 template <bool VEC4>
@@ -467,7 +543,7 @@ __global__ void polyak_kernel(float* __restrict__ ema, const float* __restrict__
 using namespace ccvsq;
 
 namespace ccvsq {
-// *e_max (if given) must already be zero
+// e_max[0..1] (if given) must already be zero
 int prepare_codebook_launch(const float* E, int K, int D, float* e_sq, void* E_bf16, float* e_max, cudaStream_t st) {
   const int K_pad = E_bf16 ? ccvsq_codebook_rows(K) : K;
   const int wpb = 8;
@@ -483,7 +559,7 @@ extern "C" int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq,
   CCVSQ_REQUIRE(E && e_sq, CCVSQ_NULL_POINTER, "prepare_codebook: E and e_sq must be non-null");
   CCVSQ_REQUIRE(K > 0 && D > 0, CCVSQ_BAD_SHAPE, "prepare_codebook: K=%d D=%d", K, D);
   cudaStream_t st = (cudaStream_t)stream;
-  if (e_max) CCVSQ_CUDA(cudaMemsetAsync(e_max, 0, sizeof(float), st));
+  if (e_max) CCVSQ_CUDA(cudaMemsetAsync(e_max, 0, 2 * sizeof(float), st));
   return prepare_codebook_launch(E, K, D, e_sq, E_bf16, e_max, st);
 }
 
@@ -600,6 +676,35 @@ extern "C" int ccvsq_code_stats(const float* x, ccvsq_layout lay, const float* E
   StreamArgs a = {};
   a.x = x; a.E = E; a.idx = idx; a.resid = resid; a.counts = counts; a.sub = sub; a.K = K;
   return stream_launch(MODE_STATS, a, L, (cudaStream_t)stream);
+}
+
+extern "C" int ccvsq_code_stats_fixed(const float* x, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
+                                      float sub, int64_t* acc, float* amax_scratch, float* resid, int32_t* counts,
+                                      void* stream) {
+  CCVSQ_REQUIRE(x && idx && acc && amax_scratch && resid, CCVSQ_NULL_POINTER, "code_stats_fixed: null pointer");
+  CCVSQ_REQUIRE(sub == 0.f || E, CCVSQ_NULL_POINTER, "code_stats_fixed: E required when sub != 0");
+  CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "code_stats_fixed: K=%d", K);
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t kd = (size_t)K * L.D;
+  CCVSQ_CUDA(cudaMemsetAsync(acc, 0, kd * sizeof(int64_t), st));
+  CCVSQ_CUDA(cudaMemsetAsync(amax_scratch, 0, sizeof(float), st));
+  const size_t nx = (size_t)L.P * L.C;
+  int blocks = cdiv((int64_t)nx, 256 * 8);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  absmax_kernel<<<blocks, 256, 0, st>>>(x, nx, sub != 0.f ? E : nullptr, kd, (unsigned int*)amax_scratch);
+  CCVSQ_LAUNCH_CHECK();
+  const size_t smem = tile_smem_bytes(L);
+  if (int rc = enable_smem(code_stats_fixed_kernel, smem)) return rc;
+  code_stats_fixed_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, st>>>(x, L, E, K, idx, sub, amax_scratch,
+                                                                   (unsigned long long*)acc, counts);
+  CCVSQ_LAUNCH_CHECK();
+  int cb = cdiv((int64_t)kd, 256 * 4);
+  if (cb > kNumSMs * 8) cb = kNumSMs * 8;
+  fixed_to_float_kernel<<<cb, 256, 0, st>>>((const long long*)acc, kd, sub, L.N, amax_scratch, resid);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
 }
 
 extern "C" int ccvsq_gather(const int64_t* code, const float* E, int K, ccvsq_layout out_lay, float* out,

@@ -18,19 +18,21 @@ from ._lib import Layout
 
 _L = _lib.load()  # fail loudly at import time if the extension is missing
 
-# Screening margin in units of 2^-8 * ||z|| * max||e|| (see ccvsq_screen).  Both operands of every product are rounded
-# to BF16 (relative error <= 2^-8 each), so ONE score errs by at most 2 * 2^-8 * sum_j |z_j e_kj| <= 2^-7 ||z|| ||e_k||,
-# and the FP32 winner can trail the BF16 maximum by at most the error of TWO scores: 4 * 2^-8 * ||z|| max||e||.
-# tau = 4 is therefore the PROVEN bound (the true winner always survives the screen, up to FP32 accumulation noise
-# ~2^-22 ||z|| ||e||); tau = 1 is ~30 standard deviations of the rounding noise for dense D = 256 vectors but can be
-# beaten by adversarial inputs (tests/test_gpu_parity.py::test_adversarial_margin).
-DEFAULT_MARGIN_TAU = 4.0
+# Screening margin (see ccvsq_screen).  A code survives the BF16 screen if its score is within
+#     margin_n = tau * 2 * (||z_n - bf16(z_n)|| * max||e|| * (1 + 2^-8) + ||z_n|| * max_k||e_k - bf16(e_k)||) + 2^-13 ||z_n|| max||e||
+# of the row maximum.  With tau = 1 this is a PROVEN bound on how far the FP32 winner can trail the BF16 maximum:
+# score errors are sum_j (dz_j e_kj + z_j de_kj + dz_j de_kj), so two scores differ from their exact values by at most
+# ||dz|| ||e_A - e_B|| + ||z|| (||de_A|| + ||de_B||) + second order (Cauchy-Schwarz), and the last term covers the FP32
+# accumulation of the tensor core.  The rounding-error norms are MEASURED (per row by the loader warps, per codebook by
+# ccvsq_prepare_codebook), so dense latents pay ~1.4 x 2^-8 ||z|| max||e|| while operands sitting on BF16 rounding
+# midpoints (tests/test_gpu_hardening.py::test_adversarial_margin) automatically get up to 4 x 2^-8 ||z|| max||e||.
+DEFAULT_MARGIN_TAU = 1.0
 
 # kernels enqueued by each entry point (ccvsq_prepare_codebook: + one 4-byte memset node)
 _KERNELS_PER_CALL = {
     "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_trace": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
     "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1, "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1,
-    "ccvsq_finalize": 1, "ccvsq_ema_update": 2,
+    "ccvsq_finalize": 1, "ccvsq_ema_update": 2, "ccvsq_code_stats_fixed": 3,
     "ccvsq_gather_add": 1, "ccvsq_polyak": 1,
     "ccvsq_quantize_forward": 0, "ccvsq_quantize_backward": 0,   # composites: counted by their wrappers
 }
@@ -166,7 +168,7 @@ class PreparedCodebook:
     weight: torch.Tensor          # [K, D] fp32 (the live parameter's storage)
     e_sq: torch.Tensor            # [K] fp32
     e_bf16: Optional[torch.Tensor]  # [codebook_rows(K), D + 16] bf16: codes | bias split (hi, mid, lo) | zeros
-    e_max: Optional[torch.Tensor]   # [1] fp32 = max ||e||
+    e_max: Optional[torch.Tensor]   # [2] fp32 = max ||e||, max ||e - bf16(e)||
     version: int
     ptr: int
 
@@ -197,7 +199,7 @@ def prepare_codebook(weight: torch.Tensor, with_bf16: Optional[bool] = None) -> 
     e_bf16 = e_max = None
     if with_bf16:
         e_bf16 = torch.empty(codebook_rows(K), D + 16, dtype=torch.bfloat16, device=dev)
-        e_max = torch.empty(1, dtype=torch.float32, device=dev)
+        e_max = torch.empty(2, dtype=torch.float32, device=dev)
     _call("ccvsq_prepare_codebook", _ptr(w), K, D, _ptr(e_sq), _ptr(e_bf16), _ptr(e_max), _stream(dev))
     return PreparedCodebook(w, e_sq, e_bf16, e_max, weight._version, w.data_ptr())
 
@@ -404,6 +406,20 @@ def code_stats(x: torch.Tensor, lay: Layout, weight: Optional[torch.Tensor], K: 
     return resid, counts
 
 
+def code_stats_fixed(x: torch.Tensor, lay: Layout, weight: Optional[torch.Tensor], K: int, idx: torch.Tensor,
+                     sub: float = 1.0, want_counts: bool = False, out: Optional[torch.Tensor] = None):
+    """Deterministic `code_stats`: 64-bit fixed-point accumulation (order-independent, run-to-run bit-identical)."""
+    dev = x.device
+    D = lay.dim
+    acc = torch.empty(K * D, dtype=torch.int64, device=dev)
+    amax = torch.empty(1, dtype=torch.float32, device=dev)
+    resid = out if out is not None else torch.empty(K, D, dtype=torch.float32, device=dev)
+    counts = torch.zeros(K, dtype=torch.int32, device=dev) if want_counts else None
+    _call("ccvsq_code_stats_fixed", _ptr(x), lay, _ptr(weight), K, _ptr(idx), float(sub), _ptr(acc), _ptr(amax), _ptr(resid),
+          _ptr(counts), _stream(dev))
+    return resid, counts
+
+
 def finalize(K: int, D: int, M: float, N: float, beta: float, resid=None, counts=None, sq_err=None, g_loss=None,
              want_dE: bool = False, want_loss: bool = False, want_perplexity: bool = False):
     ref = next(t for t in (resid, counts, sq_err, g_loss) if t is not None)
@@ -513,11 +529,17 @@ def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: f
 
 def quantize_backward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, idx: torch.Tensor,
                       g_zq: Optional[torch.Tensor], g_loss: torch.Tensor, beta: float, want_dz: bool = True,
-                      want_dE: bool = True):
+                      want_dE: bool = True, deterministic: bool = False):
     """Autograd backward of quantize.py:55-64 in one pass over z (ccvsq_quantize_backward):
     dz = g_zq + (2 g/M)(z - E[idx]);  dE = -(2 beta g/M) sum_{idx=k}(z - E[k])."""
     dev = z.device
     K, D = weight.shape
+    if deterministic and want_dE:
+        # dz is a pure elementwise map; the per-code sums take the fixed-point route (bit-identical run to run)
+        dz = backward_dz(z, lay, weight, idx, g_zq, g_loss) if want_dz else None
+        resid, _ = code_stats_fixed(z, lay, weight, K, idx, sub=1.0)
+        dE, _, _ = finalize(K, D, float(z.numel()), float(lay.rows), beta, resid=resid, g_loss=g_loss, want_dE=True)
+        return dz, dE
     dz = torch.empty_like(z) if want_dz else None
     dE = torch.empty(K, D, dtype=torch.float32, device=dev) if want_dE else None   # doubles as the resid scratch
     _call("ccvsq_quantize_backward", _ptr(z), lay, _ptr(weight), K, _ptr(idx), _ptr(g_zq), _ptr(g_loss), float(beta),

@@ -117,11 +117,15 @@ class _QuantizeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, weight, module):
         lay = ops.layout_of(z.shape, module.e_dim, module.mult)
+        want_resid = getattr(module, "_want_resid", False)
+        resid_out = getattr(module, "_resid_out", None)
+        det = module.deterministic and (want_resid or resid_out is not None)
         out = ops.quantize_forward(z, lay, weight, module.beta, module.search_mode, module.n_cand, module.margin_tau,
                                    module.exact_fallback, cb=module._cb_cached(),
-                                   want_resid=getattr(module, "_want_resid", False),
-                                   resid_out=getattr(module, "_resid_out", None))
+                                   want_resid=want_resid and not det, resid_out=None if det else resid_out)
         zq, loss, idx, perp, counts = out.zq, out.loss, out.idx, out.perplexity, out.counts
+        if det:      # EMA statistics in fixed point (a second pass over z instead of riding on the assign pass)
+            out.resid, _ = ops.code_stats_fixed(z, lay, weight.detach(), weight.shape[0], idx, sub=1.0, out=resid_out)
         module._last_resid = out.resid        # per-code residual sums for the EMA update (None unless asked for)
         ctx.lay = lay
         ctx.beta = module.beta
@@ -144,7 +148,8 @@ class _QuantizeFn(torch.autograd.Function):
         if not (want_dz or want_dE):
             return None, None, None
         g = None if (g_zq is None or not want_dz) else g_zq.to(torch.float32).contiguous()
-        dz, dE = ops.quantize_backward(z, lay, weight, idx, g, g_loss, ctx.beta, want_dz, want_dE)
+        dz, dE = ops.quantize_backward(z, lay, weight, idx, g, g_loss, ctx.beta, want_dz, want_dE,
+                                       deterministic=ctx.module.deterministic)
         ctx.module._after_backward()
         return dz, dE, None
 
@@ -217,13 +222,15 @@ class VectorQuantizer(nn.Module):
     - search_mode: 'auto' (tensor-core screen + FP32 rescoring when the shape allows, exact FP32
       kernel otherwise), 'tensor', or 'exact'
     - n_cand: candidate slots per latent kept by the screen (<= 8)
-    - margin_tau: screening margin in units of 2^-8 * ||z|| * max||e|| (default 4 = the proven worst-case bound for the
-      difference of two BF16-operand scores, ops.DEFAULT_MARGIN_TAU)
+    - margin_tau: multiplier of the screening margin; 1 (default) = the proven bound on the BF16 rounding error of a
+      score difference, see ops.DEFAULT_MARGIN_TAU / ccvsq_screen
     - exact_fallback: rows with more than n_cand codes inside the margin are re-searched exactly
+    - deterministic: accumulate the per-code sums behind `embedding.weight.grad` (and the EMA statistics) in 64-bit
+      fixed point instead of FP32 atomics: run-to-run bit-identical gradients, at the cost of a second pass over z
     """
 
     def __init__(self, n_e, e_dim, beta, mult=1, normalize=False, *, search_mode: str = "auto", n_cand: int = 4,
-                 margin_tau: float = ops.DEFAULT_MARGIN_TAU, exact_fallback: bool = True):
+                 margin_tau: float = ops.DEFAULT_MARGIN_TAU, exact_fallback: bool = True, deterministic: bool = False):
         super().__init__()
         self.n_e = n_e
         assert e_dim % mult == 0
@@ -235,6 +242,7 @@ class VectorQuantizer(nn.Module):
         self.n_cand = n_cand
         self.margin_tau = margin_tau
         self.exact_fallback = exact_fallback
+        self.deterministic = deterministic     # per-code sums (dE, EMA statistics) in 64-bit fixed point: bit-identical runs
 
         self.embedding = nn.Embedding(self.n_e, self.e_dim)
         if self.e_dim <= 1:

@@ -73,8 +73,9 @@ const char* ccvsq_last_error(void); /* thread-local, valid until the next failin
  *            -0.5*||e_k||^2, the rest zero; padding rows are zero with a bias of -3e38.  The screen
  *            multiplies the 16 extra columns with a constant (1,1,1,0,...) block, so the bias is
  *            added by the tensor core itself.
- *   e_max    [1]     fp32   out (may be NULL): max_k ||e_k||                                   */
-int ccvsq_codebook_rows(int K); /* K rounded up so that a sweep with either screen tile width (96 / 64) fits */
+ *   e_max    [2]     fp32   out (may be NULL): max_k ||e_k||, max_k ||e_k - bf16(e_k)|| (the codebook's own BF16
+ *            rounding error, which enters the screening margin)                                  */
+int ccvsq_codebook_rows(int K); /* K rounded up so that a sweep with any screen tile width (128 / 96 / 64) fits */
 int ccvsq_prepare_codebook(const float* E, int K, int D, float* e_sq, void* E_bf16, float* e_max,
                            void* stream);
 
@@ -91,9 +92,13 @@ int ccvsq_search_exact(const float* z, ccvsq_layout lay, const float* E, const f
  * latents resident in tensor memory, FP32 accumulation) with a fused running candidate selection
  * per row.  z is the caller's FP32 tensor in any ccvsq_layout (no packing pass).  A code is a
  * candidate of row n if its score is within
- *     margin_n = margin_tau * 2^-8 * ||z_n|| * (*e_max)
- * of the row maximum (tau = 1 is the first-order bound on the BF16 rounding error of one score for
- * vectors with evenly spread energy; e_max NULL = 1).
+ *     margin_n = margin_tau * 2 * (||z_n - bf16(z_n)|| * e_max[0] * (1 + 2^-8) + ||z_n|| * e_max[1])
+ *                + 2^-13 * ||z_n|| * e_max[0]
+ * of the row maximum.  With margin_tau = 1 this BOUNDS how far the FP32 winner can trail the BF16 maximum (the error
+ * of the difference of two scores whose operands are both rounded to BF16, by Cauchy-Schwarz, plus the FP32
+ * accumulation of the tensor core); the two rounding-error norms are measured (per row by the kernel, per codebook
+ * by ccvsq_prepare_codebook), so dense operands pay ~1.4 * 2^-8 ||z|| max||e|| and operands on BF16 rounding
+ * midpoints up to 4 * 2^-8 ||z|| max||e||.  e_max NULL = (1, 2^-8).
  *   idx         [N] int64 : the only candidate of the row (final), or the best BF16 candidate of a
  *                           queued row (provisional)
  *   queue_count [1] int32, zeroed by the caller: rows queued for ccvsq_rescore, i.e. rows with more
@@ -197,6 +202,18 @@ int ccvsq_backward_dz(const float* z, ccvsq_layout lay, const float* E, int K, c
  *   resid [K, D] fp32, counts [K] int32 (may be NULL).                                          */
 int ccvsq_code_stats(const float* x, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
                      float sub, float* resid, int32_t* counts, void* stream);
+
+/* Deterministic variant of ccvsq_code_stats (run-to-run bit-identical resid, whatever order the CTAs run in).  The FP32
+ * reductions of ccvsq_code_stats / ccvsq_quantize_backward are order-dependent in their last bits; here every term
+ * x_n - sub*E[k] is rounded ONCE to a 64-bit fixed-point grid 2^-s (s chosen on the device from max|x|, max|E| and N so
+ * that N terms cannot overflow) and accumulated with integer atomics, which are associative.  Three small launches
+ * (absmax, accumulate, convert); slower than the fused FP32 path, meant for reproducibility runs.
+ *   acc          int64 [K*D] scratch (zeroed by the call)
+ *   amax_scratch fp32  [1]   scratch (zeroed by the call)
+ *   resid        fp32  [K, D] out (overwritten);  counts int32 [K] (may be NULL), ADDED to            */
+int ccvsq_code_stats_fixed(const float* x, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
+                           float sub, int64_t* acc, float* amax_scratch, float* resid, int32_t* counts,
+                           void* stream);
 
 /* ---- finalize: codebook gradient, loss, perplexity -------------------------------------------
  *   dE[k,:]   = -(2*beta/M) * g_loss * resid[k,:]           (dE may be NULL)

@@ -133,8 +133,17 @@ def test_screen_scores_and_candidates(shape, K, D, cta_group):
     torch.testing.assert_close(bias, -0.5 * (cb.to(DEV) ** 2).sum(1), rtol=1e-6, atol=0)
     assert bool((pcb.e_bf16[K:, D] < -1e38).all()) and bool((pcb.e_bf16[K:, :D] == 0).all())
 
-    sd = ops.screen_debug(z.to(DEV), lay, pcb, n_cand=8, margin_tau=4.0, cta_group=cta_group, dump_scores=True)
-    torch.testing.assert_close(sd.margin, 4.0 * 2.0 ** -8 * rows.norm(dim=1) * cb.norm(dim=1).max().to(DEV), rtol=1e-5, atol=0)
+    tau = 3.0
+    sd = ops.screen_debug(z.to(DEV), lay, pcb, n_cand=8, margin_tau=tau, cta_group=cta_group, dump_scores=True)
+    # margin = tau * 2 (||dz|| max||e|| (1 + 2^-8) + ||z|| max||de||) + 2^-13 ||z|| max||e||, d. = the BF16 rounding error
+    cbd = cb.to(DEV)
+    emax = cbd.norm(dim=1).max()
+    demax = (cbd - cbd.to(torch.bfloat16).float()).norm(dim=1).max()
+    torch.testing.assert_close(pcb.e_max, torch.stack([emax, demax]), rtol=1e-5, atol=0)
+    dz = (rows - rows.to(torch.bfloat16).float()).norm(dim=1)
+    want = tau * 2 * (dz * emax * (1 + 2.0 ** -8) + rows.norm(dim=1) * demax) + 2.0 ** -13 * rows.norm(dim=1) * emax
+    torch.testing.assert_close(sd.margin, want, rtol=2e-5, atol=0)
+    assert float((sd.margin / (2.0 ** -8 * rows.norm(dim=1) * emax)).median()) < 1.6 * tau     # dense data: ~1.4 old units per tau
     s = rows.to(torch.bfloat16).float() @ pcb.e_bf16[:K, :D].float().t() + bias
     # FP32 accumulation order differs between the tensor core and torch.matmul: |s| ~ 1e2 -> 2e-2
     torch.testing.assert_close(sd.scores[:, :K], s, rtol=1e-4, atol=2e-2)
