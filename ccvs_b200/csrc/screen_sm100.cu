@@ -334,7 +334,7 @@ __host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg, int b
   s.slot_bytes = (s.slot_tx + 1023u) & ~1023u;
   const uint32_t norm_bytes = 2 * 2 * 2 * BM * 4;   // [A buffer][loader half][||z||^2, ||z - bf16(z)||^2][row]
   const uint32_t cblk_bytes = bn == 128 ? BM * 32 : 0;
-  const uint32_t fixed = nepg * LIST_BYTES + norm_bytes + nepg * BM * 4 + nepg * BM * 8 + cblk_bytes + 512;
+  const uint32_t fixed = nepg * LIST_BYTES + norm_bytes + nepg * BM * 4 + nepg * BM * 16 + cblk_bytes + 512;
   int n = (int)((227u * 1024u - fixed) / s.slot_bytes);
   s.nslots = n > MAX_SLOTS ? MAX_SLOTS : n;
   uint32_t off = 0;
@@ -342,7 +342,7 @@ __host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg, int b
   s.list = off;  off += nepg * LIST_BYTES;          // per epilogue group { [entry][row] float4 | [entry][row] u32 }
   s.norm = off;  off += norm_bytes;
   s.drop = off;  off += nepg * BM * 4;              // [group][row] best score dropped from an overflowing list
-  s.epst = off;  off += nepg * BM * 8;              // [group][row] {entries, running max} published at the end of a sweep
+  s.epst = off;  off += nepg * BM * 16;             // [group][row] {running max, best code, codes inside the margin, entries}: end-of-sweep exchange
   s.cblk = off;  off += cblk_bytes;                 // constant A block (1,1,1,0,...) of the bias step: [2 K-chunks][128 rows][16 B]
   s.bars = off;  off += 512;
   s.total = off;
@@ -528,7 +528,7 @@ __device__ __forceinline__ void load_chunk(float (&v)[32], const float* __restri
 }
 
 // 32 FP32 values -> 16 packed BF16 pairs (RN), accumulating ||v||^2 and the squared rounding error ||v - bf16(v)||^2
-__device__ __forceinline__ void pack_chunk(const float (&v)[32], uint32_t (&pk)[16], float& ss, float& dd) {
+__device__ __forceinline__ void pack_chunk(const float (&v)[32], uint32_t (&pk)[16], float& ss, float& dd, bool with_dd = true) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float a = v[2 * i], b = v[2 * i + 1];
@@ -537,9 +537,11 @@ __device__ __forceinline__ void pack_chunk(const float (&v)[32], uint32_t (&pk)[
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);                           // .x (low half) = even k
     const uint32_t bits = *reinterpret_cast<uint32_t*>(&t);
     pk[i] = bits;
-    const float da = a - __uint_as_float(bits << 16), db = b - __uint_as_float(bits & 0xffff0000u);
-    dd = fmaf(da, da, dd);
-    dd = fmaf(db, db, dd);
+    if (with_dd) {
+      const float da = a - __uint_as_float(bits << 16), db = b - __uint_as_float(bits & 0xffff0000u);
+      dd = fmaf(da, da, dd);
+      dd = fmaf(db, db, dd);
+    }
   }
 }
 
@@ -557,7 +559,9 @@ __global__ void __launch_bounds__(screen_threads(BN), 1)
 screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_ext,
               const float* __restrict__ z, const Lay L, const float* __restrict__ e_max, float tau,
               int K_pad, int n_tiles, int dblk, int nacc, int abuf_n, int n_cand, int num_group_tiles,
-              const ScreenOut out) {
+              const ScreenOut out, const int ablate) {
+  // `ablate` (CCVSQ_SCREEN_ABLATE, timing experiments only, results are WRONG when set): bit 0 = no end-of-sweep
+  // finalisation, bit 1 = no candidate slow path, bit 2 = loaders skip the rounding-error norm
   using Cfg = ScreenCfg<BN>;
   constexpr bool WIDE = Cfg::WIDE;
   constexpr int NEPG = Cfg::NEPG;
@@ -787,13 +791,13 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         if (c + 1 < nchunk) load_chunk(vb, p + (int64_t)(c + 1) * 32 * L.S, L.S, valid);
         {
           uint32_t pk[16];
-          pack_chunk(va, pk, ss, dd);
+          pack_chunk(va, pk, ss, dd, !(ablate & 4));
           tmem_st16(dst + c * 16, pk);
         }
         if (c + 1 < nchunk) {
           if (c + 2 < nchunk) load_chunk(va, p + (int64_t)(c + 2) * 32 * L.S, L.S, valid);
           uint32_t pk[16];
-          pack_chunk(vb, pk, ss, dd);
+          pack_chunk(vb, pk, ss, dd, !(ablate & 4));
           tmem_st16(dst + (c + 1) * 16, pk);
         }
       }
@@ -870,7 +874,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 8; ++i) gm[i] = fmaxf(fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), v[4 * i + 2]), v[4 * i + 3]);
           const float m = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(fmaxf(gm[3], gm[4]), gm[5]), fmaxf(gm[6], gm[7])));
-          if (m >= runmax - margin) {
+          if (m >= runmax - margin && !(ablate & 2)) {
             // a maximum that beats the old one by more than the margin makes every listed entry stale
             if (m > runmax + margin) cnt = 0;
             runmax = fmaxf(runmax, m);
@@ -939,25 +943,71 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       }
 
       if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 4 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 7] = clock64(); }
+      if (ablate & 1) continue;
       if constexpr (WIDE) {
-        // the two groups of a lane quadrant publish {entries, running max}, meet, and split the 32 rows between them
-        const uint32_t st0 = smem_base + lay.epst + (uint32_t)row_in_tile * 8u;
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st0 + (uint32_t)g * BM * 8u), "r"(cnt), "r"(__float_as_uint(runmax)) : "memory");
+        // End of the sweep.  The two groups of a lane quadrant (a) exchange their running maxima, (b) scan their OWN
+        // list against the final threshold with all 32 lanes (inline, a handful of entries), (c) exchange the partial
+        // results; the rows are then split between the two warps: a row with exactly one code inside the margin is
+        // final right here (the common case), anything else goes through the general two-list finalize_row.
+        const uint32_t st_own = smem_base + lay.epst + (uint32_t)(g * BM + row_in_tile) * 16u;
+        const uint32_t st_par = smem_base + lay.epst + (uint32_t)((1 - g) * BM + row_in_tile) * 16u;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_own), "f"(runmax) : "memory");
+        if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 3);
+        named_bar_sync(1 + q, 64);
+        float rm_par;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rm_par) : "r"(st_par));
+        const float rmax = fmaxf(runmax, rm_par), thr = rmax - margin;
+        uint32_t within = 0;
+        float best_s = -INFINITY;
+        int best_i = -1;
+#pragma unroll 1
+        for (uint32_t e = 0; e < cnt; ++e) {
+          float sc[4];
+          uint32_t code;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            within += (sc[u] >= thr) ? 1u : 0u;
+            const bool better = sc[u] > best_s;          // entries are in increasing code order: first of equals wins
+            best_s = better ? sc[u] : best_s;
+            best_i = better ? (int)code + u : best_i;
+          }
+        }
+        {
+          float dm;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dm) : "r"(drop_addr));
+          if (dm >= thr) within |= 0x80000000u;          // an overflowed list dropped a code that may be inside the margin
+        }
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_own + 4u), "r"(best_i) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_own + 8u), "r"(within), "r"(cnt) : "memory");
+        if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 4);
         named_bar_sync(1 + q, 64);
         if ((lane >> 4) == g && row < L.N) {
-          uint32_t n0, m0, n1, m1;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(n0), "=r"(m0) : "r"(st0));
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(n1), "=r"(m1) : "r"(st0 + BM * 8u));
-          RowLists rl;
-          const uint32_t l0 = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
-          rl.sc[0] = l0;              rl.co[0] = l0 - (uint32_t)row_in_tile * 12u + CO_OFFSET;
-          rl.sc[1] = l0 + LIST_BYTES; rl.co[1] = rl.co[0] + LIST_BYTES;
-          rl.n[0] = n0; rl.n[1] = n1;
-          rl.drop[0] = smem_base + lay.drop + (uint32_t)row_in_tile * 4u;
-          rl.drop[1] = rl.drop[0] + BM * 4u;
-          finalize_row<2>(rl, fmaxf(__uint_as_float(m0), __uint_as_float(m1)), margin, n_cand, row, out);
+          uint32_t w_p, n_p;
+          int bi_p;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bi_p) : "r"(st_par + 4u));
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w_p), "=r"(n_p) : "r"(st_par + 8u));
+          const uint32_t w_all = within + w_p;           // bit 31 (a dropped code) survives the sum of two small counts
+          bool done = false;
+          if (w_all == 1u && !out.dbg_cand) {            // exactly one code inside the margin, nothing dropped: final
+            if (out.idx) out.idx[row] = within == 1u ? best_i : bi_p;
+            done = true;
+          }
+          if (!done) {
+            RowLists rl;
+            const uint32_t l0 = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
+            rl.sc[0] = l0;              rl.co[0] = l0 - (uint32_t)row_in_tile * 12u + CO_OFFSET;
+            rl.sc[1] = l0 + LIST_BYTES; rl.co[1] = rl.co[0] + LIST_BYTES;
+            rl.n[g] = cnt; rl.n[1 - g] = n_p;
+            rl.drop[0] = smem_base + lay.drop + (uint32_t)row_in_tile * 4u;
+            rl.drop[1] = rl.drop[0] + BM * 4u;
+            finalize_row<2>(rl, rmax, margin, n_cand, row, out);
+          }
         }
+        if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 5);
         named_bar_sync(1 + q, 64);              // the partner has read this group's list: it may be reused
+        if (q == 0) CCVSQ_TILE_STAMP(tl, 9 + 2 * g, 3);
       } else {
         if (row < L.N) {
           RowLists rl;
@@ -1052,8 +1102,9 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
   const int n_tiles = (K + BN - 1) / BN;          // rows [K, n_tiles*BN) of the shadow are padding (bias -3e38)
   CCVSQ_REQUIRE(n_tiles * BN <= K_pad, CCVSQ_BAD_SHAPE, "screen: codebook shadow has %d rows, the sweep needs %d",
                 K_pad, n_tiles * BN);
+  static const int ablate = [] { const char* e = getenv("CCVSQ_SCREEN_ABLATE"); return e ? atoi(e) : 0; }();
   CCVSQ_CUDA(cudaLaunchKernelEx(&cfg, kern, mb, mx, z, L, e_max, tau, K_pad, n_tiles, dblk, nacc, abuf,
-                                n_cand, (int)group_tiles, out));
+                                n_cand, (int)group_tiles, out, ablate));
   return CCVSQ_OK;
 }
 

@@ -143,7 +143,7 @@ def test_screen_scores_and_candidates(shape, K, D, cta_group):
     dz = (rows - rows.to(torch.bfloat16).float()).norm(dim=1)
     want = tau * 2 * (dz * emax * (1 + 2.0 ** -8) + rows.norm(dim=1) * demax) + 2.0 ** -13 * rows.norm(dim=1) * emax
     torch.testing.assert_close(sd.margin, want, rtol=2e-5, atol=0)
-    assert float((sd.margin / (2.0 ** -8 * rows.norm(dim=1) * emax)).median()) < 1.6 * tau     # dense data: ~1.4 old units per tau
+    assert float((sd.margin / (2.0 ** -8 * rows.norm(dim=1) * emax)).median()) < 2.0 * tau     # dense data: ~1.7 x 2^-8 ||z|| max||e|| per tau
     s = rows.to(torch.bfloat16).float() @ pcb.e_bf16[:K, :D].float().t() + bias
     # FP32 accumulation order differs between the tensor core and torch.matmul: |s| ~ 1e2 -> 2e-2
     torch.testing.assert_close(sd.scores[:, :K], s, rtol=1e-4, atol=2e-2)
