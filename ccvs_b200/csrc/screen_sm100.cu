@@ -292,16 +292,19 @@ constexpr int BM = 128;              // latent rows per CTA (TMEM lanes)
 //        handed back as soon as both have issued their loads, and each has two tile times for its max trees / lists.
 //   96   long sweeps (K >= 2304): three accumulators, one A buffer
 //   64   D = 512 / fallback plans
-constexpr int LCAP = 16;             // candidate-list entries (groups of 4 codes) per row and epilogue group
-constexpr int LKEEP = LCAP - 8;      // one slow path appends up to 8 groups: compact down to this many first
-// candidate list in shared memory: entry e of a row = 4 raw scores at sc_base + e*ENT_STRIDE (sc_base = list +
-// row*16) and the first code of the group at co_base + e*ENT_STRIDE (co_base = list + BM*16 + row*4): ONE stride
-// for both halves, so an append computes a single address per group
-constexpr uint32_t ENT_STRIDE = BM * 16 + BM * 4;
-constexpr uint32_t SC_STRIDE = ENT_STRIDE;
-constexpr uint32_t CO_STRIDE = ENT_STRIDE;
-constexpr uint32_t CO_OFFSET = BM * 16;
-constexpr uint32_t LIST_BYTES = LCAP * ENT_STRIDE;
+// Candidate store in shared memory ("chunk parking").  A 32-column chunk whose maximum reaches (running max - margin)
+// is parked whole: 8 unpredicated 128-bit stores + one header {first code, chunk maximum}.  Every lane of a warp sets
+// ~ln(chunks) running-max records per sweep, so SOME lane is in that case for most chunks and the warp pays the
+// parking path almost always: it has to be short (about 25 instructions; the per-group lists of round 1 cost ~100
+// with prefix sums, predicated stores and compaction).  A new maximum that beats the old one by more than the margin
+// makes everything parked so far stale (ring restarts); otherwise the ring overwrites its oldest entry and remembers
+// the largest maximum it dropped, so a row is only flagged if a dropped chunk could still hold a code inside the final
+// margin.  Entry e of a group: scores [8 x float4][128 rows] (a warp's store of one float4 is 512 contiguous bytes),
+// then headers [128 rows] x {code, max}.
+constexpr uint32_t ENTRY_BYTES = 8 * BM * 16 + BM * 8;
+constexpr uint32_t HDR_OFFSET = 8 * BM * 16;
+// entries per row and epilogue group (the same shared memory per row for the one-group and the two-group plans)
+__host__ __device__ constexpr int park_cap(int bn) { return bn == 128 ? 3 : 6; }
 constexpr int MAX_SLOTS = 16;
 // tensor-memory columns (32-bit):
 //   BN < 128 : [0, nacc*BN) accumulators | [nacc*BN, +8) bias-extension A block | then abuf_n A buffers of D/2
@@ -320,7 +323,7 @@ struct ScreenCfg {
 __host__ __device__ constexpr int screen_threads(int bn) { return bn == 128 ? 640 : 512; }
 
 struct ScreenSmem {
-  uint32_t slots, list, norm, drop, epst, cblk, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
+  uint32_t slots, list, norm, epst, cblk, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
   uint32_t block_bytes, ext_off, slot_bytes, slot_tx;
   int nslots;
 };
@@ -332,70 +335,21 @@ __host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg, int b
   s.ext_off = dblk * s.block_bytes;                 // bias extension: [2 K-chunks][rows][16 B]
   s.slot_tx = s.ext_off + rows * 32;
   s.slot_bytes = (s.slot_tx + 1023u) & ~1023u;
-  const uint32_t norm_bytes = 2 * 2 * 2 * BM * 4;   // [A buffer][loader half][||z||^2, ||z - bf16(z)||^2][row]
+  const uint32_t norm_bytes = 2 * 2 * 2 * BM * 4 + 2 * BM * 8;   // [A buffer][loader half][||z||^2, ||z - bf16(z)||^2][row] | [group][row] {live running max, sweep}
   const uint32_t cblk_bytes = bn == 128 ? BM * 32 : 0;
-  const uint32_t fixed = nepg * LIST_BYTES + norm_bytes + nepg * BM * 4 + nepg * BM * 16 + cblk_bytes + 512;
+  const uint32_t list_bytes = (uint32_t)park_cap(bn) * ENTRY_BYTES;      // per epilogue group
+  const uint32_t fixed = nepg * list_bytes + norm_bytes + nepg * BM * 16 + cblk_bytes + 512;
   int n = (int)((227u * 1024u - fixed) / s.slot_bytes);
   s.nslots = n > MAX_SLOTS ? MAX_SLOTS : n;
   uint32_t off = 0;
   s.slots = off; off += (uint32_t)s.nslots * s.slot_bytes;
-  s.list = off;  off += nepg * LIST_BYTES;          // per epilogue group { [entry][row] float4 | [entry][row] u32 }
+  s.list = off;  off += nepg * list_bytes;          // per epilogue group: park_cap entries (see ENTRY_BYTES)
   s.norm = off;  off += norm_bytes;
-  s.drop = off;  off += nepg * BM * 4;              // [group][row] best score dropped from an overflowing list
   s.epst = off;  off += nepg * BM * 16;             // [group][row] {running max, best code, codes inside the margin, entries}: end-of-sweep exchange
   s.cblk = off;  off += cblk_bytes;                 // constant A block (1,1,1,0,...) of the bias step: [2 K-chunks][128 rows][16 B]
   s.bars = off;  off += 512;
   s.total = off;
   return s;
-}
-
-// Candidate list maintenance (rare path).  Drops entries whose best score fell below `thr`; if
-// more than LKEEP survive, the entries with the lowest best score go too and the best dropped
-// score is remembered (drop_addr: one float per row in shared memory), so the row is flagged only if
-// a dropped code could still be inside the final margin.  Returns the new entry count.  Everything
-// is passed by value: the caller's list state stays in registers.
-__device__ __noinline__ uint32_t list_compact(uint32_t sc_base, uint32_t co_base, uint32_t n, float thr,
-                                              uint32_t drop_addr) {
-  uint32_t w = 0;
-  for (uint32_t e = 0; e < n; ++e) {
-    float a, b, c, d;
-    uint32_t code;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(sc_base + e * SC_STRIDE));
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
-    if (fmaxf(fmaxf(a, b), fmaxf(c, d)) >= thr) {
-      if (w != e) {
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sc_base + w * SC_STRIDE), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(co_base + w * CO_STRIDE), "r"(code) : "memory");
-      }
-      ++w;
-    }
-  }
-  while (w > LKEEP) {
-    float lo = INFINITY;              // victim: lowest best score, highest code among equals
-    uint32_t lo_code = 0, lo_e = 0;
-    for (uint32_t e = 0; e < w; ++e) {
-      float a, b, c, d;
-      uint32_t code;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(sc_base + e * SC_STRIDE));
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
-      const float mx = fmaxf(fmaxf(a, b), fmaxf(c, d));
-      if (mx < lo || (mx == lo && code > lo_code)) { lo = mx; lo_code = code; lo_e = e; }
-    }
-    float dm;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dm) : "r"(drop_addr));
-    dm = fmaxf(dm, lo);
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(drop_addr), "f"(dm) : "memory");
-    --w;
-    for (uint32_t e = lo_e; e < w; ++e) {   // close the hole, keeping entries in increasing code order
-      float a, b, c, d;
-      uint32_t code;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(sc_base + (e + 1) * SC_STRIDE));
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + (e + 1) * CO_STRIDE));
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sc_base + e * SC_STRIDE), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(co_base + e * CO_STRIDE), "r"(code) : "memory");
-    }
-  }
-  return w;
 }
 
 struct ScreenOut {
@@ -416,47 +370,96 @@ struct ScreenOut {
 };
 constexpr int TRACE_SWEEPS = 32;
 
-// the candidate lists of one row: one per epilogue group (the wide-tile plan keeps two, each over half the columns)
+// the parked chunks of one row: one ring per epilogue group (the wide-tile plan keeps two, each over half the columns)
 struct RowLists {
-  uint32_t sc[2], co[2], n[2], drop[2];
+  uint32_t base[2];      // shared-memory address of the group's entry 0, already offset to this row's float4 column
+  uint32_t hdr[2];       // ... and of its header
+  uint32_t n[2];         // valid entries
 };
 
-// Candidates of one row once all codes have been seen: every listed code with score >= runmax -
-// margin, sorted by (score desc, code asc), at most n_cand of them.  Rows with exactly one
-// candidate are final; the others are queued for FP32 re-scoring.  Kept out of line (and rolled) so
-// the per-tile loop stays small in the instruction cache.
+// scan the live entries (chunk maximum >= thr) of one ring: count of codes inside the margin, best (score, lowest code)
+__device__ __forceinline__ void scan_ring(uint32_t base, uint32_t hdr, uint32_t n, float thr, uint32_t& within,
+                                          float& best_s, int& best_i) {
+#pragma unroll 1
+  for (uint32_t e = 0; e < n; ++e) {
+    uint32_t code;
+    float mx;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(code), "=f"(mx) : "r"(hdr + e * ENTRY_BYTES));
+    if (!(mx >= thr)) continue;
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+      float sc[4];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3])
+                   : "r"(base + e * ENTRY_BYTES + (uint32_t)i * (BM * 16)));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {      // (padding codes carry -3e38 and never pass)
+        const int c = (int)code + 4 * i + u;
+        within += (sc[u] >= thr) ? 1u : 0u;
+        const bool better = sc[u] > best_s || (sc[u] == best_s && c < best_i);   // lowest code among equal scores
+        best_s = better ? sc[u] : best_s;
+        best_i = better ? c : best_i;
+      }
+    }
+  }
+}
+
+// Fast end-of-sweep scan of one store: how many parked codes are inside the margin, and — valid only when that number
+// is exactly one — which code it is.  Per live chunk: the 8 group maxima (FMNMX3 trees), the number of groups that reach
+// the threshold, and, if that is one, the four scores of that group again (one more shared-memory load).  Two or more
+// qualifying groups are reported as "at least two codes" — the caller takes the general path then.
+__device__ __forceinline__ void scan_unique(uint32_t base, uint32_t hdr, uint32_t n, float thr, uint32_t& within,
+                                            uint32_t& code_sum) {
+#pragma unroll 1
+  for (uint32_t e = 0; e < n; ++e) {
+    uint32_t code;
+    float mx;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(code), "=f"(mx) : "r"(hdr + e * ENTRY_BYTES));
+    if (!(mx >= thr)) continue;
+    const uint32_t eb = base + e * ENTRY_BYTES;
+    uint32_t ng = 0, gi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float sc[4];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3])
+                   : "r"(eb + (uint32_t)i * (BM * 16)));
+      const bool p = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), sc[2]), sc[3]) >= thr;
+      ng += p ? 1u : 0u;
+      gi += p ? (uint32_t)i : 0u;
+    }
+    if (ng == 1u) {
+      float sc[4];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3])
+                   : "r"(eb + gi * (BM * 16)));
+      uint32_t w = 0, off = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool p = sc[u] >= thr;
+        w += p ? 1u : 0u;
+        off += p ? (uint32_t)u : 0u;
+      }
+      within += w;
+      code_sum += w * (code + 4u * gi) + off;
+    } else {
+      within += 2u;            // (ng >= 2; ng == 0 cannot happen: the chunk maximum reached the threshold)
+    }
+  }
+}
+
+// General end-of-sweep path of one row (rows with more than one code inside the margin, dropped chunks, diagnostics):
+// every parked code with score >= runmax - margin, sorted by (score desc, code asc), at most n_cand of them, goes to the
+// re-scoring queue.  Kept out of line (and rolled) so the per-tile loop stays small in the instruction cache.
 template <int NL>
-__device__ __noinline__ void finalize_row(const RowLists L2, float runmax, float margin, int n_cand, int64_t row,
-                                          const ScreenOut out) {
+__device__ __noinline__ void finalize_row(const RowLists L2, float runmax, float margin, bool dropped, int n_cand,
+                                          int64_t row, const ScreenOut out) {
   const float thr = runmax - margin;
-  float dropped_max = -FLT_MAX;
   uint32_t within = 0;
   float best_s = -INFINITY;
   int best_i = -1;
 #pragma unroll
-  for (int l = 0; l < NL; ++l) {             // (unrolled: the struct stays in registers)
-    float dm;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dm) : "r"(L2.drop[l]));
-    dropped_max = fmaxf(dropped_max, dm);
-#pragma unroll 1
-    for (uint32_t e = 0; e < L2.n[l]; ++e) {
-      float sc[4];
-      uint32_t code;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(L2.sc[l] + e * SC_STRIDE));
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(L2.co[l] + e * CO_STRIDE));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {      // branch-free (padding codes carry -3e38 and never pass)
-        within += (sc[u] >= thr) ? 1u : 0u;
-        const int i = (int)code + u;
-        const bool better = sc[u] > best_s || (sc[u] == best_s && i < best_i);   // lowest code among equal scores
-        best_s = better ? sc[u] : best_s;
-        best_i = better ? i : best_i;
-      }
-    }
-  }
-  const uint8_t flag = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped_max >= thr ? 2 : 0));
+  for (int l = 0; l < NL; ++l) scan_ring(L2.base[l], L2.hdr[l], L2.n[l], thr, within, best_s, best_i);
+  const uint8_t flag = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped ? 2 : 0));
   const bool final_row = within == 1 && flag == 0;
-  // (a row of NaN / Inf latents lists nothing: every returned index stays inside [0, K) like torch.argmin's)
+  // (a row of NaN / Inf latents parks nothing: every returned index stays inside [0, K) like torch.argmin's)
   if (out.idx) out.idx[row] = best_i < 0 ? 0 : best_i;
   if (final_row && !out.dbg_cand) return;
 
@@ -481,17 +484,23 @@ __device__ __noinline__ void finalize_row(const RowLists L2, float runmax, float
       for (int l = 0; l < NL; ++l) {
 #pragma unroll 1
         for (uint32_t e = 0; e < L2.n[l]; ++e) {
-          float sc[4];
           uint32_t code;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(L2.sc[l] + e * SC_STRIDE));
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(L2.co[l] + e * CO_STRIDE));
+          float mx;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(code), "=f"(mx) : "r"(L2.hdr[l] + e * ENTRY_BYTES));
+          if (!(mx >= thr)) continue;
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            float sc[4];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3])
+                         : "r"(L2.base[l] + e * ENTRY_BYTES + (uint32_t)i * (BM * 16)));
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = (int)code + u;
-            const float x = sc[u];
-            const bool after_prev = (x < prev_s) || (x == prev_s && i > prev_i);
-            const bool better = (x > bs_) || (x == bs_ && i < bi);
-            if (x >= thr && after_prev && better) { bs_ = x; bi = i; }
+            for (int u = 0; u < 4; ++u) {
+              const int ci = (int)code + 4 * i + u;
+              const float x = sc[u];
+              const bool after_prev = (x < prev_s) || (x == prev_s && ci > prev_i);
+              const bool better = (x > bs_) || (x == bs_ && ci < bi);
+              if (x >= thr && after_prev && better) { bs_ = x; bi = ci; }
+            }
           }
         }
       }
@@ -559,9 +568,16 @@ __global__ void __launch_bounds__(screen_threads(BN), 1)
 screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_ext,
               const float* __restrict__ z, const Lay L, const float* __restrict__ e_max, float tau,
               int K_pad, int n_tiles, int dblk, int nacc, int abuf_n, int n_cand, int num_group_tiles,
-              const ScreenOut out, const int ablate) {
-  // `ablate` (CCVSQ_SCREEN_ABLATE, timing experiments only, results are WRONG when set): bit 0 = no end-of-sweep
-  // finalisation, bit 1 = no candidate slow path, bit 2 = loaders skip the rounding-error norm
+              const ScreenOut out, const int ablate_arg) {
+  // Ablation switches for timing experiments (results are WRONG when set; compiled in only with -DCCVSQ_ENABLE_ABLATE,
+  // then read from CCVSQ_SCREEN_ABLATE): bit 0 = no end-of-sweep work, bit 1 = no chunk parking, bit 2 = loaders skip the
+  // rounding-error norm, bit 3 / bit 7 = loaders skip all / half of the tensor-memory stores, bit 4 = loaders skip the
+  // global loads, bit 5 = no end-of-sweep scan, bit 6 = no end-of-sweep barriers.  profiles/r02_screen_history.md
+#ifdef CCVSQ_ENABLE_ABLATE
+  const int ablate = ablate_arg;
+#else
+  constexpr int ablate = 0;
+#endif
   using Cfg = ScreenCfg<BN>;
   constexpr bool WIDE = Cfg::WIDE;
   constexpr int NEPG = Cfg::NEPG;
@@ -633,6 +649,13 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       tmem_st8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + TM_EXT, ext);
       tmem_st_wait();
       tc_fence_before();
+    }
+  }
+  if constexpr (WIDE) {
+    // live running-max words of the two epilogue groups: no sweep yet (uninitialised shared memory could carry tag 0)
+    if (warp >= Cfg::EP_WARP0 && warp < Cfg::LD_WARP0) {
+      const uint32_t w = smem_base + lay.norm + 2 * 2 * 2 * BM * 4 + (uint32_t)(threadIdx.x - Cfg::EP_WARP0 * 32) * 8u;
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(w), "r"(__float_as_uint(-FLT_MAX)), "r"(0xffffffffu) : "memory");
     }
   }
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -772,7 +795,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
       const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
       const int64_t n = ((int64_t)gt * CG + rank) * BM + r;
-      const bool valid = n < L.N;
+      const bool valid = n < L.N && !(ablate & 16);
       const float* p = z;
       if (valid) {
         const int64_t pos = n / L.mult;
@@ -792,13 +815,13 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         {
           uint32_t pk[16];
           pack_chunk(va, pk, ss, dd, !(ablate & 4));
-          tmem_st16(dst + c * 16, pk);
+          if (!(ablate & 8)) tmem_st16(dst + c * 16, pk);
         }
         if (c + 1 < nchunk) {
           if (c + 2 < nchunk) load_chunk(va, p + (int64_t)(c + 2) * 32 * L.S, L.S, valid);
           uint32_t pk[16];
           pack_chunk(vb, pk, ss, dd, !(ablate & 4));
-          tmem_st16(dst + (c + 1) * 16, pk);
+          if (!(ablate & (8 | 128))) tmem_st16(dst + (c + 1) * 16, pk);
         }
       }
       tmem_st_wait();
@@ -820,9 +843,21 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     // of every tile and keeps its own running maximum / candidate list; the two lists meet in finalize_row.
     const int q = warp & 3, g = (warp - Cfg::EP_WARP0) >> 2;
     const int row_in_tile = q * 32 + lane;
-    const uint32_t sc_base = smem_base + lay.list + (uint32_t)g * LIST_BYTES + (uint32_t)row_in_tile * 16u;
-    const uint32_t co_base = sc_base - (uint32_t)row_in_tile * 16u + CO_OFFSET + (uint32_t)row_in_tile * 4u;
-    const uint32_t drop_addr = smem_base + lay.drop + (uint32_t)(g * BM + row_in_tile) * 4u;
+    constexpr uint32_t CAP = (uint32_t)park_cap(BN);
+    constexpr uint32_t LIST_BYTES = CAP * ENTRY_BYTES;            // one group's store
+    const uint32_t pk_base = smem_base + lay.list + (uint32_t)g * LIST_BYTES + (uint32_t)row_in_tile * 16u;   // entry 0, float4 0
+    const uint32_t pk_hdr = smem_base + lay.list + (uint32_t)g * LIST_BYTES + HDR_OFFSET + (uint32_t)row_in_tile * 8u;
+    // wide plan: the two groups of a row tell each other their running maxima once per tile (plain shared-memory words):
+    // a group stops parking noise as soon as the OTHER half of the columns has produced the row's winner
+    // (each word carries the sweep number it belongs to: the two groups are not in lock step across sweep boundaries,
+    //  and a value from another sweep is another row's)
+    const uint32_t live_own = smem_base + lay.norm + 2 * 2 * 2 * BM * 4 + (uint32_t)(g * BM + row_in_tile) * 8u;
+    const uint32_t live_par = smem_base + lay.norm + 2 * 2 * 2 * BM * 4 + (uint32_t)((1 - g) * BM + row_in_tile) * 8u;
+    auto peer_running_max = [&](uint32_t sweep) {
+      uint32_t vb, tag;
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(vb), "=r"(tag) : "r"(live_par));
+      return tag == sweep ? __uint_as_float(vb) : -FLT_MAX;
+    };
     const uint32_t te_bar = (CG == 1) ? tmem_empty(0) : mapa(tmem_empty(0), 0);
     const float emax = e_max ? __ldg(e_max) : 1.f;
     const float demax = e_max ? __ldg(e_max + 1) : 0.00390625f;
@@ -843,9 +878,12 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(norm_empty(ab));
-      float runmax = -FLT_MAX;
-      uint32_t cnt = 0;                         // list entries in use
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(drop_addr), "f"(-FLT_MAX) : "memory");
+      float runmax = -FLT_MAX, dropmax = -FLT_MAX;   // running maximum; largest maximum of a chunk the store dropped
+
+      uint32_t cnt = 0;                         // parked chunks (valid entries: [0, cnt))
+      float pmax[CAP];                          // their maxima (registers: the victim of a full store is found without loads)
+#pragma unroll
+      for (uint32_t e = 0; e < CAP; ++e) pmax[e] = -FLT_MAX;
 
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(tmem_full(b), b_phase);
@@ -853,13 +891,12 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + (WIDE ? (uint32_t)g * 64u : 0u);
         const int col0 = j * BN + (WIDE ? g * 64 : 0);
+        float peer_max = -FLT_MAX;              // wide plan: the other group's running maximum (a tile old at most)
+        if constexpr (WIDE) peer_max = peer_running_max(tl);
 
-        // One 32-column chunk of this thread's row.  Fast path: maxima of the 8 groups of 4 columns (16
-        // ops) and their maximum (4 ops).  A chunk can only contribute candidates if its maximum reaches
-        // (running max - margin).  On short sweeps (K = 1024) some lane of the warp is in that case for
-        // ~85 % of the chunks (every lane sets ~ln(K/32) records plus its true winner), so the slow path
-        // is written for throughput: the slot of every qualifying group is a prefix sum of the predicates
-        // (no pointer chain, no write-after-read hazards on address registers between the stores).
+        // One 32-column chunk of this thread's row.  Fast path: maxima of the 8 groups of 4 columns (16 ops) and
+        // their maximum (4 ops).  A chunk can only contribute candidates if its maximum reaches (running max - margin);
+        // then it is parked whole (see ENTRY_BYTES).
         auto process = [&](uint32_t (&ra)[32], const int cbase) {
           float v[32];
 #pragma unroll
@@ -874,31 +911,32 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 8; ++i) gm[i] = fmaxf(fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), v[4 * i + 2]), v[4 * i + 3]);
           const float m = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(fmaxf(gm[3], gm[4]), gm[5]), fmaxf(gm[6], gm[7])));
-          if (m >= runmax - margin && !(ablate & 2)) {
-            // a maximum that beats the old one by more than the margin makes every listed entry stale
-            if (m > runmax + margin) cnt = 0;
+          if (m >= fmaxf(runmax, peer_max) - margin && !(ablate & 2)) {
+            if (m > runmax + margin) { cnt = 0; dropmax = -FLT_MAX; }   // everything parked so far is stale
             runmax = fmaxf(runmax, m);
-            const float thr = runmax - margin;
-            if (cnt > LKEEP) cnt = list_compact(sc_base, co_base, cnt, thr, drop_addr);
-            uint32_t slot[9];
-            slot[0] = 0;
+            uint32_t slot = cnt;
+            bool park = true;
+            if (cnt == CAP) {                   // store full: the chunk with the smallest maximum goes (maybe this one)
+              float lo = pmax[0];
+              slot = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) slot[i + 1] = slot[i] + (gm[i] >= thr ? 1u : 0u);
-            const uint32_t base_sc = sc_base + cnt * ENT_STRIDE, base_co = co_base + cnt * ENT_STRIDE;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              asm volatile(
-                  "{\n\t"
-                  ".reg .pred p;\n\t"
-                  "setp.ne.u32 p, %2, %3;\n\t"
-                  "@p st.shared.v4.f32 [%0], {%4, %5, %6, %7};\n\t"
-                  "@p st.shared.u32 [%1], %8;\n\t"
-                  "}"
-                  ::"r"(base_sc + slot[i] * ENT_STRIDE), "r"(base_co + slot[i] * ENT_STRIDE), "r"(slot[i + 1]), "r"(slot[i]),
-                    "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]), "r"((uint32_t)(col0 + cbase + 4 * i))
-                  : "memory");
+              for (uint32_t e = 1; e < CAP; ++e)
+                if (pmax[e] < lo) { lo = pmax[e]; slot = e; }
+              park = m > lo;
+              dropmax = fmaxf(dropmax, park ? lo : m);   // the largest maximum ever dropped decides whether the row gets flagged
+            } else {
+              ++cnt;
             }
-            cnt += slot[8];
+            if (park) {
+              const uint32_t eoff = slot * ENTRY_BYTES;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pk_base + eoff + (uint32_t)i * (BM * 16)),
+                             "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pk_hdr + eoff), "r"((uint32_t)(col0 + cbase)), "r"(__float_as_uint(m)) : "memory");
+#pragma unroll
+              for (uint32_t e = 0; e < CAP; ++e) pmax[e] = (slot == e) ? m : pmax[e];
+            }
           }
         };
 
@@ -917,6 +955,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 4);
           process(ra, 0);
           process(rb, 32);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(live_own), "r"(__float_as_uint(runmax)), "r"(tl) : "memory");   // (racy by design: any earlier value of THIS sweep is a valid lower bound)
         } else {
           // BN/32 chunks of 32 columns; the tcgen05.ld of the next chunk overlaps the max tree of this
           // one, and the accumulator is handed back as soon as the last chunk is in registers
@@ -945,75 +984,63 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 4 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 7] = clock64(); }
       if (ablate & 1) continue;
       if constexpr (WIDE) {
-        // End of the sweep.  The two groups of a lane quadrant (a) exchange their running maxima, (b) scan their OWN
-        // list against the final threshold with all 32 lanes (inline, a handful of entries), (c) exchange the partial
-        // results; the rows are then split between the two warps: a row with exactly one code inside the margin is
-        // final right here (the common case), anything else goes through the general two-list finalize_row.
+        // End of the sweep.  Each group scans its OWN store against its own threshold (all 32 lanes, inline; typically
+        // one live chunk) and publishes {running max, the code if exactly one is inside its margin, that count, entries};
+        // after ONE barrier the rows are split between the two warps of the lane quadrant: the group holding the larger
+        // maximum decides — if it has exactly one code inside the margin, dropped nothing that matters, and the other
+        // group's maximum is below the threshold, the row is final right here (the common case); anything else takes
+        // the general two-store finalize_row.
         const uint32_t st_own = smem_base + lay.epst + (uint32_t)(g * BM + row_in_tile) * 16u;
         const uint32_t st_par = smem_base + lay.epst + (uint32_t)((1 - g) * BM + row_in_tile) * 16u;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_own), "f"(runmax) : "memory");
-        if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 3);
-        named_bar_sync(1 + q, 64);
-        float rm_par;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rm_par) : "r"(st_par));
-        const float rmax = fmaxf(runmax, rm_par), thr = rmax - margin;
-        uint32_t within = 0;
-        float best_s = -INFINITY;
-        int best_i = -1;
-#pragma unroll 1
-        for (uint32_t e = 0; e < cnt; ++e) {
-          float sc[4];
-          uint32_t code;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3]) : "r"(sc_base + e * SC_STRIDE));
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(co_base + e * CO_STRIDE));
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            within += (sc[u] >= thr) ? 1u : 0u;
-            const bool better = sc[u] > best_s;          // entries are in increasing code order: first of equals wins
-            best_s = better ? sc[u] : best_s;
-            best_i = better ? (int)code + u : best_i;
-          }
-        }
+        uint32_t within = 0, code1 = 0;
         {
-          float dm;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dm) : "r"(drop_addr));
-          if (dm >= thr) within |= 0x80000000u;          // an overflowed list dropped a code that may be inside the margin
+          // threshold from the larger of the two running maxima as far as this group knows it (the peer's value may be a
+          // tile old: a LOWER threshold, i.e. a superset — and exact for the group that holds the row's maximum, whose
+          // result is the one that decides below)
+          const float thr_s = fmaxf(runmax, peer_running_max(tl)) - margin;
+          if (!(ablate & 32)) scan_unique(pk_base, pk_hdr, cnt, thr_s, within, code1); else within = 1;
+          if (dropmax >= thr_s) within |= 0x80000000u;             // a dropped chunk may hold a code inside the margin
         }
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(st_own + 4u), "r"(best_i) : "memory");
-        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_own + 8u), "r"(within), "r"(cnt) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_own), "r"(__float_as_uint(runmax)), "r"(code1), "r"(within), "r"(cnt) : "memory");
+        if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 3);
+        if (!(ablate & 64)) named_bar_sync(1 + q, 64);
         if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 4);
-        named_bar_sync(1 + q, 64);
         if ((lane >> 4) == g && row < L.N) {
-          uint32_t w_p, n_p;
-          int bi_p;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(bi_p) : "r"(st_par + 4u));
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w_p), "=r"(n_p) : "r"(st_par + 8u));
-          const uint32_t w_all = within + w_p;           // bit 31 (a dropped code) survives the sum of two small counts
-          bool done = false;
-          if (w_all == 1u && !out.dbg_cand) {            // exactly one code inside the margin, nothing dropped: final
-            if (out.idx) out.idx[row] = within == 1u ? best_i : bi_p;
-            done = true;
-          }
-          if (!done) {
+          uint32_t rm_pb, code_p, w_p, n_p;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rm_pb), "=r"(code_p), "=r"(w_p), "=r"(n_p) : "r"(st_par));
+          const float rm_p = __uint_as_float(rm_pb);
+          const bool own_max = runmax >= rm_p;
+          const float rmax = fmaxf(runmax, rm_p), thr = rmax - margin;
+          const uint32_t w_top = own_max ? within : w_p;            // count (and drop bit) of the group holding the maximum
+          if (w_top == 1u && fminf(runmax, rm_p) < thr && !out.dbg_cand) {
+            if (out.idx) out.idx[row] = (int64_t)(own_max ? code1 : code_p);
+          } else {
             RowLists rl;
-            const uint32_t l0 = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
-            rl.sc[0] = l0;              rl.co[0] = l0 - (uint32_t)row_in_tile * 12u + CO_OFFSET;
-            rl.sc[1] = l0 + LIST_BYTES; rl.co[1] = rl.co[0] + LIST_BYTES;
-            rl.n[g] = cnt; rl.n[1 - g] = n_p;
-            rl.drop[0] = smem_base + lay.drop + (uint32_t)row_in_tile * 4u;
-            rl.drop[1] = rl.drop[0] + BM * 4u;
-            finalize_row<2>(rl, rmax, margin, n_cand, row, out);
+            const uint32_t b0 = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
+            const uint32_t h0 = smem_base + lay.list + HDR_OFFSET + (uint32_t)row_in_tile * 8u;
+            rl.base[0] = b0; rl.base[1] = b0 + LIST_BYTES;
+            rl.hdr[0] = h0;  rl.hdr[1] = h0 + LIST_BYTES;
+            rl.n[g] = cnt;   rl.n[1 - g] = n_p;
+            finalize_row<2>(rl, rmax, margin, ((within | w_p) & 0x80000000u) != 0, n_cand, row, out);
           }
         }
         if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 5);
-        named_bar_sync(1 + q, 64);              // the partner has read this group's list: it may be reused
+        if (!(ablate & 64)) named_bar_sync(1 + q, 64);              // the partner has read this group's store: it may be reused
         if (q == 0) CCVSQ_TILE_STAMP(tl, 9 + 2 * g, 3);
       } else {
         if (row < L.N) {
-          RowLists rl;
-          rl.sc[0] = sc_base; rl.co[0] = co_base; rl.n[0] = cnt; rl.drop[0] = drop_addr;
-          rl.sc[1] = rl.co[1] = rl.n[1] = rl.drop[1] = 0;
-          finalize_row<1>(rl, runmax, margin, n_cand, row, out);
+          const float thr = runmax - margin;
+          uint32_t within = 0, best_i = 0;
+          scan_unique(pk_base, pk_hdr, cnt, thr, within, best_i);
+          const bool dropped = dropmax >= thr;
+          if (within == 1u && !dropped && !out.dbg_cand) {
+            if (out.idx) out.idx[row] = (int64_t)best_i;
+          } else {
+            RowLists rl;
+            rl.base[0] = pk_base; rl.hdr[0] = pk_hdr; rl.n[0] = cnt;
+            rl.base[1] = rl.hdr[1] = rl.n[1] = 0;
+            finalize_row<1>(rl, runmax, margin, dropped, n_cand, row, out);
+          }
         }
       }
     }
@@ -1116,7 +1143,7 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
 struct ScreenPlan { int bn, nacc, abuf; };
 static bool plan_fits(int D, int bn, int nacc, int abuf) {
   const int a_cols = D / 2;
-  if (bn == 128) return nacc == 2 && 2 * 128 + abuf * a_cols <= (int)TMEM_COLS;
+  if (bn == 128) return nacc == 2 && D <= 256 && 2 * 128 + abuf * a_cols <= (int)TMEM_COLS;   // (D = 512: one B slot left)
   return nacc * bn + 8 + abuf * a_cols <= (int)TMEM_COLS;
 }
 static ScreenPlan plan_screen(int K, int D) {
