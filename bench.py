@@ -101,11 +101,16 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(workload: str, device, seed: int):
-    """Distribution T: E ~ N(0,1); z = E[randint] + 0.5 N(0,1) laid out [clips, frames, C, h, w]."""
+def make_inputs(workload: str, device, seed: int, cb_seed=None):
+    """Distribution T: E ~ N(0,1); z = E[randint] + 0.5 N(0,1) laid out [clips, frames, C, h, w].
+    `cb_seed`: seed of the codebook when it differs from the latents' (multi-GPU: the codebook is replicated, every
+    rank draws its own latents around the SAME codes)."""
     (clips, frames), D, h, w, K, _ = WORKLOADS[workload]
     g = torch.Generator(device=device).manual_seed(seed)
-    cb = torch.randn(K, D, generator=g, device=device)
+    if cb_seed is None or cb_seed == seed:
+        cb = torch.randn(K, D, generator=g, device=device)
+    else:
+        cb = torch.randn(K, D, generator=torch.Generator(device=device).manual_seed(cb_seed), device=device)
     n = clips * frames * h * w
     z = torch.empty(clips, frames, D, h, w, device=device)
     # build frame by frame blocks to bound temporary memory
@@ -256,6 +261,7 @@ def train_record(args, dev, world, cb, z, barrier):
     from ccvs_b200.quantize import EMAVectorQuantizer
     K, D = cb.shape
     n_lat = z.numel() // D
+    cb = cb.clone()                        # (replicated codebook: make_inputs draws it from the same seed on every rank)
     g_out = torch.randn_like(z)
     zt = z.detach().clone().requires_grad_(True)
     res = {}
@@ -456,13 +462,15 @@ def main():
     host_affinity = "not requested" if args.no_numa_bind else bind_near_gpu(local_rank)
     import torch.distributed as dist
     if world > 1:
+        if os.environ.get("CCVSQ_BENCH_NCCL_HIGH_PRIORITY"):       # (A/B switch: measured no better, see profiles/)
+            os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     from ccvs_b200 import VectorQuantizer, ops
     from ccvs_b200.quantize import EMAVectorQuantizer
 
     (clips, frames), D, h, w_, K, desc = WORKLOADS[args.workload]
-    z, cb, n_lat = make_inputs(args.workload, dev, 1234 + rank)
+    z, cb, n_lat = make_inputs(args.workload, dev, 1234 + rank, cb_seed=1234)
     train = args.workload == "train"
     if train:
         vq = EMAVectorQuantizer(K, D, 0.25, decay=0.99, search_mode=args.search_mode).to(dev).train()

@@ -52,7 +52,7 @@ class ForwardArgs(Structure):
         ("header", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_uint64),
         ("idx", c_void_p), ("zq", c_void_p), ("loss", c_void_p), ("perplexity", c_void_p),
         ("ev_search_begin", c_void_p), ("ev_search_end", c_void_p),
-        ("resid", c_void_p),
+        ("resid", c_void_p), ("counts_f32", c_void_p),
     ]
 
 
@@ -86,6 +86,7 @@ SIGNATURES = {
     "ccvsq_code_stats_fixed": (c_int, [_P, Layout, _P, c_int, _P, c_float, _P, _P, _P, _P, _P]),
     "ccvsq_finalize": (c_int, [_P, _P, _P, _P, c_int, c_int, c_double, c_double, c_float, _P, _P, _P, _P]),
     "ccvsq_ema_update": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
+    "ccvsq_ema_update_packed": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
     "ccvsq_gather_add": (c_int, [_P, _P, c_int, c_int, c_int64, _P, c_int64, _P, _P, _P]),
     "ccvsq_polyak": (c_int, [_P, _P, c_int64, c_double, _P]),
     "ccvsq_forward_workspace_bytes": (c_uint64, [c_int64, c_int, c_int, c_int, c_int, c_int]),

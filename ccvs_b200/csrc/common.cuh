@@ -139,6 +139,7 @@ struct FinArgs {          // loss / perplexity folded into the assign kernel (la
   int32_t* ticket;        // zeroed by the caller
   float* loss;
   float* perplexity;
+  float* counts_f32;      // optional [K]: the per-code counts as FP32 (tail of a packed all-reduce buffer)
   double M, N;
   float beta;
 };

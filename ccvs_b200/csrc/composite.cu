@@ -121,6 +121,7 @@ extern "C" int ccvsq_quantize_forward(const ccvsq_forward_args* a, void* stream)
   s.fin.ticket = ticket;
   s.fin.loss = a->loss;
   s.fin.perplexity = a->perplexity;
+  s.fin.counts_f32 = a->counts_f32;
   s.fin.M = (double)L.P * L.C;
   s.fin.N = (double)L.N;
   s.fin.beta = a->beta;

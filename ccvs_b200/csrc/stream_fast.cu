@@ -65,7 +65,9 @@ __device__ void fold_finalize(const StreamArgs& a, unsigned total_ctas, bool* s_
   if (a.fin.perplexity && a.counts) {
     float acc = 0.f;
     for (int k = threadIdx.x; k < a.K; k += FNT) {
-      const float p = (float)((double)__ldcg(a.counts + k) / a.fin.N);
+      const int32_t c = __ldcg(a.counts + k);
+      if (a.fin.counts_f32) a.fin.counts_f32[k] = (float)c;   // exact below 2^24 per code
+      const float p = (float)((double)c / a.fin.N);
       acc += p * logf(p + 1e-10f);                      // quantize.py:68
     }
     acc = warp_sum(acc);

@@ -456,7 +456,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* resid,   /* 
                                                        const float* __restrict__ g_loss, int K, int D,
                                                        double M, double N, float beta,
                                                        float* dE, float* __restrict__ loss,
-                                                       float* __restrict__ perplexity) {
+                                                       float* __restrict__ perplexity,
+                                                       float* __restrict__ counts_f32 = nullptr) {
   if (dE && resid) {
     const float coef = -(float)(2.0 * (double)beta / M) * __ldg(g_loss);
     const size_t total = (size_t)K * D;
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* resid,   /* 
     __shared__ float red[8];
     float acc = 0.f;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      if (counts_f32) counts_f32[k] = (float)counts[k];
       const float p = (float)((double)counts[k] / N);
       acc += p * logf(p + 1e-10f);   // quantize.py:68
     }
@@ -491,7 +493,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* resid,   /* 
 // ------------------------------------------------------------------------------------------------
 // EMA codebook update (extension, see header)
 // ------------------------------------------------------------------------------------------------
-__global__ void ema_counts_kernel(float* __restrict__ n_ema, const int32_t* __restrict__ counts, int K,
+template <typename CT>
+__global__ void ema_counts_kernel(float* __restrict__ n_ema, const CT* __restrict__ counts, int K,
                                   float decay, float* __restrict__ n_total) {
   __shared__ float red[8];
   float acc = 0.f;
@@ -510,9 +513,10 @@ __global__ void ema_counts_kernel(float* __restrict__ n_ema, const int32_t* __re
   }
 }
 
+template <typename CT>
 __global__ void ema_embed_kernel(float* __restrict__ E, const float* __restrict__ n_ema,
                                  float* __restrict__ sum_ema, const float* __restrict__ resid,
-                                 const int32_t* __restrict__ counts, int K, int D, float decay,
+                                 const CT* __restrict__ counts, int K, int D, float decay,
                                  float eps, const float* __restrict__ n_total) {
   const size_t total = (size_t)K * D;
   const float nt = *n_total;
@@ -634,7 +638,7 @@ int stream_launch(int mode, const StreamArgs& a, const Lay& L, cudaStream_t st) 
   // the generic assign kernel has no folded finalize: one extra (tiny) launch
   if (mode == MODE_ASSIGN && a.fin.ticket && (a.fin.loss || a.fin.perplexity)) {
     finalize_kernel<<<1, 256, 0, st>>>(nullptr, a.counts, a.sq_err, nullptr, a.K, L.D, a.fin.M, a.fin.N, a.fin.beta,
-                                      nullptr, a.fin.loss, a.fin.perplexity);
+                                      nullptr, a.fin.loss, a.fin.perplexity, a.fin.counts_f32);
     CCVSQ_LAUNCH_CHECK();
   }
   return CCVSQ_OK;
@@ -760,18 +764,30 @@ extern "C" int ccvsq_finalize(const float* resid, const int32_t* counts, const d
   return CCVSQ_OK;
 }
 
-extern "C" int ccvsq_ema_update(float* E, float* n_ema, float* sum_ema, const float* resid,
-                                const int32_t* counts, int K, int D, float decay, float eps,
-                                float* scratch, void* stream) {
+template <typename CT>
+static int ema_update_impl(float* E, float* n_ema, float* sum_ema, const float* resid, const CT* counts, int K, int D,
+                           float decay, float eps, float* scratch, void* stream) {
   CCVSQ_REQUIRE(E && n_ema && sum_ema && resid && counts && scratch, CCVSQ_NULL_POINTER,
                 "ema_update: null pointer");
   CCVSQ_REQUIRE(K > 0 && D > 0, CCVSQ_BAD_SHAPE, "ema_update: K=%d D=%d", K, D);
   cudaStream_t st = (cudaStream_t)stream;
-  ema_counts_kernel<<<1, 256, 0, st>>>(n_ema, counts, K, decay, scratch);
+  ema_counts_kernel<CT><<<1, 256, 0, st>>>(n_ema, counts, K, decay, scratch);
   CCVSQ_LAUNCH_CHECK();
   int blocks = cdiv((int64_t)K * D, 256 * 4);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  ema_embed_kernel<<<blocks, 256, 0, st>>>(E, n_ema, sum_ema, resid, counts, K, D, decay, eps, scratch);
+  ema_embed_kernel<CT><<<blocks, 256, 0, st>>>(E, n_ema, sum_ema, resid, counts, K, D, decay, eps, scratch);
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_ema_update(float* E, float* n_ema, float* sum_ema, const float* resid,
+                                const int32_t* counts, int K, int D, float decay, float eps,
+                                float* scratch, void* stream) {
+  return ema_update_impl<int32_t>(E, n_ema, sum_ema, resid, counts, K, D, decay, eps, scratch, stream);
+}
+
+extern "C" int ccvsq_ema_update_packed(float* E, float* n_ema, float* sum_ema, const float* packed, int K, int D,
+                                       float decay, float eps, float* scratch, void* stream) {
+  CCVSQ_REQUIRE(packed, CCVSQ_NULL_POINTER, "ema_update_packed: null pointer");
+  return ema_update_impl<float>(E, n_ema, sum_ema, packed, packed + (size_t)K * D, K, D, decay, eps, scratch, stream);
 }

@@ -82,7 +82,8 @@ def start_reduce_ema_stats(buf: torch.Tensor, counts: torch.Tensor, K: int, D: i
     """First half of `reduce_ema_stats`: pack the counts and ISSUE the all-reduce without making the current stream
     wait for it (NCCL runs it on its own stream, ordered after the work already enqueued on the current one).
     Returns the work handle (None when there is nothing to reduce)."""
-    buf[K * D:].copy_(counts)
+    if counts is not None:          # (None: the forward already wrote the fp32 counts into the buffer's tail)
+        buf[K * D:].copy_(counts)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=True)
     return None

@@ -32,7 +32,7 @@ DEFAULT_MARGIN_TAU = 1.0
 _KERNELS_PER_CALL = {
     "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_trace": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
     "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1, "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1,
-    "ccvsq_finalize": 1, "ccvsq_ema_update": 2, "ccvsq_code_stats_fixed": 3,
+    "ccvsq_finalize": 1, "ccvsq_ema_update": 2, "ccvsq_ema_update_packed": 2, "ccvsq_code_stats_fixed": 3,
     "ccvsq_gather_add": 1, "ccvsq_polyak": 1,
     "ccvsq_quantize_forward": 0, "ccvsq_quantize_backward": 0,   # composites: counted by their wrappers
 }
@@ -465,7 +465,7 @@ class ForwardOut:
 def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: float, mode: str = "auto", n_cand: int = 4,
                      margin_tau: float = DEFAULT_MARGIN_TAU, exact_fallback: bool = True, cb: Optional[PreparedCodebook] = None,
                      indices_only: bool = False, want_resid: bool = False,
-                     resid_out: Optional[torch.Tensor] = None) -> ForwardOut:
+                     resid_out: Optional[torch.Tensor] = None, counts_f32_out: Optional[torch.Tensor] = None) -> ForwardOut:
     """The whole forward of quantize.py:32-74 in one call of the C ABI (ccvsq_quantize_forward).
     `cb` = cached codebook side data (frozen codebook); None rebuilds it inside the call."""
     _req(z, torch.float32, "z")
@@ -509,6 +509,8 @@ def quantize_forward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, beta: f
         elif want_resid:
             resid = torch.empty(K, D, dtype=torch.float32, device=dev)
             a.resid = resid.data_ptr()
+        if counts_f32_out is not None:     # fp32 copy of the usage counts (tail of the packed all-reduce buffer)
+            a.counts_f32 = _req(counts_f32_out, torch.float32, "counts_f32_out").data_ptr()
     name = "ccvsq_screen" if tensor else "ccvsq_search_exact"
     timed = PROFILER.timing is True or (PROFILER.timing and name in PROFILER.timing)
     if timed:   # the dominant search kernel is bracketed by events recorded inside the C call
@@ -547,6 +549,15 @@ def quantize_backward(z: torch.Tensor, lay: Layout, weight: torch.Tensor, idx: t
     fused = fast_stream_layout(lay)
     PROFILER.launches += (1 if fused or not (want_dz and want_dE) else 2) * int(want_dz or want_dE) + int(want_dE)
     return dz, dE
+
+
+def ema_update_packed(weight: torch.Tensor, n_ema: torch.Tensor, sum_ema: torch.Tensor, packed: torch.Tensor,
+                      decay: float, eps: float) -> None:
+    """`ema_update` straight from the packed statistics buffer [resid: K*D | counts: K] fp32 (after the all-reduce)."""
+    K, D = weight.shape
+    scratch = torch.empty(1, dtype=torch.float32, device=weight.device)
+    _call("ccvsq_ema_update_packed", _ptr(weight), _ptr(n_ema), _ptr(sum_ema), _ptr(packed), K, D, float(decay), float(eps),
+          _ptr(scratch), _stream(weight.device))
 
 
 def ema_update(weight: torch.Tensor, n_ema: torch.Tensor, sum_ema: torch.Tensor, resid: torch.Tensor,

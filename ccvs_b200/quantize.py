@@ -122,7 +122,8 @@ class _QuantizeFn(torch.autograd.Function):
         det = module.deterministic and (want_resid or resid_out is not None)
         out = ops.quantize_forward(z, lay, weight, module.beta, module.search_mode, module.n_cand, module.margin_tau,
                                    module.exact_fallback, cb=module._cb_cached(),
-                                   want_resid=want_resid and not det, resid_out=None if det else resid_out)
+                                   want_resid=want_resid and not det, resid_out=None if det else resid_out,
+                                   counts_f32_out=getattr(module, "_counts_f32_out", None))
         zq, loss, idx, perp, counts = out.zq, out.loss, out.idx, out.perplexity, out.counts
         if det:      # EMA statistics in fixed point (a second pass over z instead of riding on the assign pass)
             out.resid, _ = ops.code_stats_fixed(z, lay, weight.detach(), weight.shape[0], idx, sub=1.0, out=resid_out)
@@ -133,12 +134,15 @@ class _QuantizeFn(torch.autograd.Function):
         # the EMA variant rewrites the codebook in place right after forward: keep the version the
         # indices were computed with for backward
         ctx.save_for_backward(z, weight.detach().clone() if module._inplace_codebook_update else weight, idx)
+        ctx.token = module._begin_deferred() if hasattr(module, "_begin_deferred") else None
         ctx.mark_non_differentiable(idx, perp, counts)
         return zq, loss, idx, perp, counts
 
     @staticmethod
     def backward(ctx, g_zq, g_loss, _gi, _gp, _gc):
         z, weight, idx = ctx.saved_tensors
+        if ctx.token is not None:       # the codebook this forward used, if it was rewritten before this backward ran
+            weight = getattr(ctx.module, "_stale_codebooks", {}).pop(ctx.token, weight)
         lay = ctx.lay
         dev = z.device
         if g_loss is None:
@@ -150,7 +154,7 @@ class _QuantizeFn(torch.autograd.Function):
         g = None if (g_zq is None or not want_dz) else g_zq.to(torch.float32).contiguous()
         dz, dE = ops.quantize_backward(z, lay, weight, idx, g, g_loss, ctx.beta, want_dz, want_dE,
                                        deterministic=ctx.module.deterministic)
-        ctx.module._after_backward()
+        ctx.module._after_backward(ctx.token)
         return dz, dE, None
 
 
@@ -253,12 +257,9 @@ class VectorQuantizer(nn.Module):
         self._inplace_codebook_update = False
         self.last_counts: Optional[torch.Tensor] = None   # int32 [K] usage of the last forward
 
-    def _after_backward(self):
+    def _after_backward(self, token=None):
         """Called by `_QuantizeFn.backward` once its kernels are enqueued (the EMA variant completes its deferred
         statistics exchange here)."""
-        sync = getattr(self, "sync_codebook", None)
-        if sync is not None:
-            sync()
 
     # -- codebook side data (||e||^2, BF16 shadow, bias).  Rebuilt on EVERY call by default: the
     # reference's Polyak averaging writes `param.data` in place (quantized_video_model.py:962-964),
@@ -545,6 +546,10 @@ class EMAVectorQuantizer(VectorQuantizer):
         self._inplace_codebook_update = True
         self._last_resid = None
         self._pending = None              # (work handle | None, packed buffer) of a deferred all-reduce + EMA update
+        self._deferring = False           # set by forward() when this call defers its codebook update
+        self._next_token = 0
+        self._outstanding = None          # token of the forward whose backward has not run yet
+        self._stale_codebooks = {}        # token -> codebook copy, for a backward that runs AFTER its update was flushed
         self.register_buffer("ema_count", torch.zeros(n_e))
         self.register_buffer("ema_sum", self.embedding.weight.detach().clone())
 
@@ -552,52 +557,73 @@ class EMAVectorQuantizer(VectorQuantizer):
         """Training forward = the reference forward + EMA statistics.  The per-code residual sums ride on the assign pass
         (one read of z); with several ranks they are accumulated straight into the packed buffer of ONE all-reduce.
 
-        Overlap (`overlap=True`, several ranks, autograd on): the all-reduce is issued asynchronously right after the
+        Overlap (`overlap=True`, autograd on): the all-reduce (several ranks) is issued asynchronously right after the
         forward's kernels; the wait and the in-place EMA update of the codebook are deferred to the end of this
-        module's backward (`_QuantizeFn.backward`), which works on the codebook copy saved by the forward — so the
-        collective runs on NCCL's stream under everything between this forward and that backward (decoder forward /
-        backward, the dz kernel) instead of sitting serially in front of them.  The update is flushed earlier by
+        module's backward (`_QuantizeFn.backward`) — so the collective runs on NCCL's stream under everything between
+        this forward and that backward (decoder forward / backward, the dz kernel) instead of sitting serially in front
+        of them, and the backward reads the live, not yet updated codebook (no per-step copy).  The update is flushed earlier by
         anything that reads the codebook through this module (next forward, embed_code, sync_codebook, state_dict)."""
         self.sync_codebook()
-        buf = None
-        self._want_resid = self.training
-        world = vq_dist.world_info()[1]
-        if self.training and self.sync and world > 1:
-            buf, self._resid_out = vq_dist.ema_stats_buffer(self.n_e, self.e_dim, z.device)
+        if not self.training:
+            return super().forward(z)
+        # always the packed buffer [resid: K*D | counts: K] fp32: the forward fills both parts itself (assign pass and its
+        # folded finalisation), the all-reduce (several ranks) and the EMA update read it as it is
+        buf, self._resid_out = vq_dist.ema_stats_buffer(self.n_e, self.e_dim, z.device)
+        self._counts_f32_out = buf[self.n_e * self.e_dim:]
+        self._want_resid = True
+        # deferred mode: the codebook is rewritten only after this module's backward has been enqueued, so the backward
+        # can use the live parameter (no per-step copy of the codebook)
+        will_defer = self.overlap and torch.is_grad_enabled() and z.requires_grad
+        self._inplace_codebook_update = not will_defer
+        self._deferring = will_defer
         try:
             out = super().forward(z)
         finally:
             self._want_resid = False
             self._resid_out = None
-        if not self.training:
-            return out
+            self._counts_f32_out = None
         with torch.no_grad():
-            resid, self._last_resid = self._last_resid, None
-            counts = self.last_counts          # per-code usage from the forward's assign kernel (zeros for an empty shard)
-            if buf is None:
-                if z.numel() == 0:
-                    return out                 # nothing was assigned: the codebook keeps its state
-                ops.ema_update(self.embedding.weight, self.ema_count, self.ema_sum, resid, counts, self.decay, self.eps)
-                return out
+            self._last_resid = None
             if z.numel() == 0:
+                if not (self.sync and vq_dist.world_info()[1] > 1):
+                    return out                 # nothing was assigned: the codebook keeps its state
                 buf.zero_()                    # an empty shard still joins the collective, with zero statistics
-            work = vq_dist.start_reduce_ema_stats(buf, counts, self.n_e, self.e_dim)
+            work = vq_dist.start_reduce_ema_stats(buf, None, self.n_e, self.e_dim) if self.sync else None
             self._pending = (work, buf)
-            deferred = self.overlap and torch.is_grad_enabled() and out[0].requires_grad
-            if not deferred:
+            if not will_defer:
                 self.sync_codebook()
         return out
+
+    def _begin_deferred(self):
+        """Token of a forward that keeps the LIVE codebook for its backward (deferred mode), else None."""
+        if not self._deferring:
+            return None
+        self._deferring = False
+        self._next_token += 1
+        self._outstanding = self._next_token
+        return self._next_token
+
+    def _after_backward(self, token=None):
+        if token is not None and token == self._outstanding:
+            self._outstanding = None
+        self.sync_codebook()
 
     @torch.no_grad()
     def sync_codebook(self):
         """Complete a deferred statistics exchange: the current stream waits for the all-reduce, then the EMA update
-        rewrites the codebook in place.  No-op when nothing is pending."""
+        rewrites the codebook in place.  No-op when nothing is pending.  If the backward of the forward that produced
+        the statistics has not run yet (gradient accumulation, a second forward first, ...), the codebook it used is
+        copied aside for it before the rewrite."""
         if self._pending is None:
             return
         work, buf = self._pending
         self._pending = None
-        resid, counts = vq_dist.finish_reduce_ema_stats(work, buf, self.n_e, self.e_dim)
-        ops.ema_update(self.embedding.weight, self.ema_count, self.ema_sum, resid, counts, self.decay, self.eps)
+        if self._outstanding is not None:
+            self._stale_codebooks[self._outstanding] = self.embedding.weight.detach().clone()
+            self._outstanding = None
+        if work is not None:
+            work.wait()            # the current STREAM waits for the collective (no host block with NCCL)
+        ops.ema_update_packed(self.embedding.weight, self.ema_count, self.ema_sum, buf, self.decay, self.eps)
 
     def embed_code(self, code, channel_major_hw=None, table=None):
         self.sync_codebook()

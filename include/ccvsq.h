@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CCVSQ_VERSION 200 /* major*100 + minor; 2.x: ccvsq_forward_args starts with struct_size */
+#define CCVSQ_VERSION 201 /* major*100 + minor; 2.x: ccvsq_forward_args starts with struct_size */
 
 typedef enum ccvsq_status {
   CCVSQ_OK = 0,
@@ -232,6 +232,10 @@ int ccvsq_finalize(const float* resid, const int32_t* counts, const double* sq_e
 int ccvsq_ema_update(float* E, float* n_ema, float* sum_ema, const float* resid,
                      const int32_t* counts, int K, int D, float decay, float eps, float* scratch,
                      void* stream);
+/* Same update from the packed statistics buffer of the multi-GPU exchange, [resid: K*D | counts: K] fp32 (what one
+ * all-reduce sums over the ranks; ccvsq_forward_args.resid / .counts_f32 fill it in the forward): no unpacking step. */
+int ccvsq_ema_update_packed(float* E, float* n_ema, float* sum_ema, const float* packed, int K, int D,
+                            float decay, float eps, float* scratch, void* stream);
 
 /* ---- whole-op entry points ---------------------------------------------------------------------
  * ccvsq_quantize_forward enqueues the complete forward of the reference module
@@ -287,6 +291,8 @@ typedef struct ccvsq_forward_args {
   float* resid;            /* optional [K, D] (zeroed by the call): resid[k,:] = sum_{idx=k} (z - E[k]), the per-code
                               statistic of an EMA codebook update, accumulated by the assign pass on its own read of z
                               (no second pass over the latents); NULL = off */
+  float* counts_f32;       /* optional [K]: the per-code usage counts written as fp32 by the pass that finalises loss /
+                              perplexity (exact below 2^24 per code): the tail of a packed all-reduce buffer; NULL = off */
 } ccvsq_forward_args;
 
 uint64_t ccvsq_forward_workspace_bytes(int64_t N, int K, int D, int search_mode, int n_cand,

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_version():
-    assert _lib.load().ccvsq_version() == 200
+    assert _lib.load().ccvsq_version() == 201
 
 
 def test_argument_validation_without_gpu():
@@ -86,9 +86,9 @@ def test_composite_argument_validation_without_gpu():
 
 
 def test_layout_struct_matches_header():
-    assert ctypes.sizeof(_lib.ForwardArgs) == 184
+    assert ctypes.sizeof(_lib.ForwardArgs) == 192
     assert _lib.ForwardArgs.struct_size.offset == 0 and _lib.ForwardArgs.z.offset == 8
-    assert _lib.ForwardArgs.resid.offset == 176
+    assert _lib.ForwardArgs.resid.offset == 176 and _lib.ForwardArgs.counts_f32.offset == 184
     assert _lib.ForwardArgs.lay.offset == 16 and _lib.ForwardArgs.e_sq.offset == 80 and _lib.ForwardArgs.idx.offset == 128
     assert ctypes.sizeof(_lib.Layout) == 24     # int64 + 3 x int32 (+4 pad)
     assert _lib.Layout.G.offset == 0 and _lib.Layout.C.offset == 8 and _lib.Layout.mult.offset == 16

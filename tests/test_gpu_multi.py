@@ -114,7 +114,10 @@ def test_ema_training_two_ranks_equal_one_gpu_on_the_whole_batch(overlap):
         full = z.grad.detach().cpu()
         for r, dz in ((0, dz0), (1, dz1)):
             ste = g_all[r * per:(r + 1) * per].cpu()
-            torch.testing.assert_close((dz[step] - ste) / 2, full[r * per:(r + 1) * per] - ste, rtol=1e-4, atol=1e-7)
+            # (the commitment term is ~1e-6 next to an O(1) straight-through term: compare it in float64, to the FP32
+            #  rounding of the sums it was extracted from)
+            torch.testing.assert_close((dz[step].double() - ste.double()) / 2, full[r * per:(r + 1) * per].double() - ste.double(),
+                                       rtol=1e-3, atol=5e-7)
     torch.testing.assert_close(vq.embedding.weight.detach().cpu(), w0, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(vq.ema_count.cpu(), n0, rtol=1e-6, atol=0)
     torch.testing.assert_close(vq.ema_sum.cpu(), s0, rtol=1e-5, atol=1e-6)

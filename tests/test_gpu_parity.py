@@ -380,6 +380,8 @@ def test_ema_update_matches_textbook():
     zc = z.to(DEV).requires_grad_(True)
     z_q, loss, (_, _, idx) = m(zc)
     assert torch.equal(idx.view(-1).cpu(), idx_ref)
+    assert torch.equal(m.embedding.weight.detach().cpu(), cb)     # deferred: the update waits for the backward ...
+    m.sync_codebook()                                             # ... or for an explicit flush
     torch.testing.assert_close(m.ema_count.cpu(), n, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(m.ema_sum.cpu(), s, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(m.embedding.weight.cpu(), new_cb, rtol=1e-4, atol=1e-5)
@@ -648,3 +650,34 @@ def test_smoke_without_programmatic_dependent_launch():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "smoke ok" in r.stdout
+
+
+def test_ema_deferred_update_keeps_the_codebook_for_a_late_backward():
+    """Deferred mode (the EMA update waits for the module's backward): a second forward before the first backward
+    flushes the pending update — the first backward must still see the codebook ITS forward used."""
+    shape, K, D = (4, 64, 8, 8), 96, 64
+    z1, cb = vq_oracle.synth(shape, K, D, "T", seed=31)
+    z2, _ = vq_oracle.synth(shape, K, D, "T", seed=32)
+    vq = EMAVectorQuantizer(K, D, 0.25, decay=0.5, sync=False, overlap=True).to(DEV).train()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+        vq.ema_sum.copy_(cb.to(DEV))
+        vq.ema_count.fill_(1.0)
+    a = z1.to(DEV).requires_grad_(True)
+    b = z2.to(DEV).requires_grad_(True)
+    w0 = vq.embedding.weight.detach().clone()
+    zq1, l1, (_, _, i1) = vq(a)
+    assert torch.equal(vq.embedding.weight.detach(), w0)          # update deferred: still the codebook of forward 1
+    zq2, l2, (_, _, i2) = vq(b)                                   # flushes update 1 (then defers update 2)
+    w1 = vq.embedding.weight.detach().clone()
+    assert not torch.equal(w1, w0)
+    l2.backward()
+    l1.backward()
+    vq.sync_codebook()
+    M = z1.numel()
+    # dz = (2 / M) (z - E_used[idx]) with the codebook each forward saw
+    torch.testing.assert_close(a.grad.cpu(), (2.0 / M) * (z1 - vq_oracle.to_channel_first(w0.cpu()[i1.view(-1).cpu()].view(4, 8, 8, D))),
+                               rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(b.grad.cpu(), (2.0 / M) * (z2 - vq_oracle.to_channel_first(w1.cpu()[i2.view(-1).cpu()].view(4, 8, 8, D))),
+                               rtol=1e-5, atol=1e-9)
+    assert not vq._stale_codebooks and vq._pending is None
