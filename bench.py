@@ -252,6 +252,49 @@ def k16384_records(dev, search_mode: str, peaks_):
     return rec, hbm
 
 
+def encoder_tail_record(dev, peaks_):
+    """the encoder's last 1x1 ConvLayer that produces the c2 latents (1024 frames, 512 -> 256 channels,
+    16x16), on the BF16x6 tcgen05 kernel, next to the FP32 library convolution (TF32 off) of the same block."""
+    from ccvs_b200 import EncoderTail
+    bf16_peak = peaks_[0]
+    G, ci, co, h, w = 1024, 512, 256, 16, 16
+    x = torch.randn(G, ci, h, w, device=dev)
+    m = EncoderTail(ci, co).to(dev)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+
+    def ours():
+        with torch.no_grad():
+            return m(x)
+
+    def lib():
+        with torch.no_grad():
+            return torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x, m.weight * m.scale, m.bias), 0.1)
+
+    def t(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    to, tl = t(ours), t(lib)
+    diff = float((ours() - lib()).abs().max())
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    flops = 2.0 * G * h * w * ci * co
+    return {"workload": "encoder tail of the c2 batch: ConvLayer(512, 256, 1) + LeakyReLU(0.1) on 262144 positions (skip_autoencoder.py:331)",
+            "ms": to, "positions_per_sec": G * h * w / (to * 1e-3), "fp32_accurate_TFLOPs": flops / to / 1e9,
+            "bf16_tensor_TFLOPs": 6 * flops / to / 1e9, "frac_of_bf16_peak": 6 * flops / to / 1e9 / bf16_peak,
+            "fp32_library_conv_ms": tl, "speedup_vs_fp32_library_conv": tl / to, "max_abs_diff_vs_library": diff,
+            "scheme": "three-term BF16 split of both operands, six tcgen05.mma per K step, leading / correction products in "
+                      "separate tensor-memory accumulators (FP32-class accuracy: tools/tail_accuracy.py)"}
+
+
 def train_record(args, dev, world, cb, z, barrier):
     """Training-mode quantizer (BASELINE configs[4]) at the c2 shape on every rank: forward + straight-through backward
     + commitment loss + EMA codebook update with ONE NCCL all-reduce of the packed code statistics per step.  Three
@@ -740,6 +783,7 @@ def main():
         # north_star targets that the default workload does not exercise (rank 0, one GPU)
         torch.cuda.empty_cache()
         line["roofline_k16384"], line["hbm_kernels_8x8"] = k16384_records(dev, args.search_mode, peaks())
+        line["encoder_tail"] = encoder_tail_record(dev, peaks())
         if not args.no_cpu_baseline:
             line["index_match"] = index_match_record(dev, args.search_mode)
     print_result(json.dumps(line))

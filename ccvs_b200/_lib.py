@@ -87,6 +87,8 @@ SIGNATURES = {
     "ccvsq_finalize": (c_int, [_P, _P, _P, _P, c_int, c_int, c_double, c_double, c_float, _P, _P, _P, _P]),
     "ccvsq_ema_update": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
     "ccvsq_ema_update_packed": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
+    "ccvsq_encoder_tail_prepare": (c_int, [_P, c_int, c_int, c_float, _P, _P]),
+    "ccvsq_encoder_tail": (c_int, [_P, c_int64, c_int, c_int, _P, _P, c_int, c_float, c_int, _P, _P]),
     "ccvsq_gather_add": (c_int, [_P, _P, c_int, c_int, c_int64, _P, c_int64, _P, _P, _P]),
     "ccvsq_polyak": (c_int, [_P, _P, c_int64, c_double, _P]),
     "ccvsq_forward_workspace_bytes": (c_uint64, [c_int64, c_int, c_int, c_int, c_int, c_int]),

@@ -35,249 +35,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace ccvsq {
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cta address -> shared::cluster address of the same offset in CTA `cta` of the cluster
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
-  return r;
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// arrive on a barrier given by a shared::cluster address (own or peer CTA).  Default (CTA-scope
-// release) semantics on purpose: what the waiter consumes is tensor-memory state ordered by
-// tcgen05.fence, and a cluster-scope release costs a GPU-wide MEMBAR (~800 cycles) per arrive.
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.  The
-// clock is consulted only every 256 failed polls so the spin costs few issue slots.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();   // ~2 s
-  }
-}
-// Long waits (a whole code sweep): let the hardware suspend the thread (try_wait with a suspend-time hint wakes
-// on the phase flip) instead of polling: a nanosleep poll loop cost a quarter of all issued instructions of the
-// kernel at K = 1024, taken from the schedulers the epilogue warps run on.
-__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-// 2-D tiled TMA load into this CTA's shared memory; `bar` is a shared::cluster barrier address (for
-// CG == 2 the leader CTA's barrier collects the bytes of both halves).
-template <int CG>
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  if constexpr (CG == 1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-  } else {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-  }
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T, BF16 x BF16 -> FP32.  The shared-memory descriptor is passed as
-// two 32-bit halves so that advancing it is a single 32-bit add on the (warp-uniform) low word.
-template <int CG>
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t b_desc_hi,
-                                        uint32_t idesc, uint32_t accumulate) {
-  if constexpr (CG == 1) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-// D[tmem] (+)= A[smem] * B[smem]^T (SS form): used for the one bias step of the wide-tile plan, whose constant A block
-// lives in shared memory because 2 x 128 accumulator columns + 2 A buffers fill all 512 tensor-memory columns
-template <int CG>
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_desc_lo, uint32_t a_desc_hi, uint32_t b_desc_lo,
-                                        uint32_t b_desc_hi, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (CG == 1) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 ad, {%1, %2};\n\tmov.b64 bd, {%3, %4};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_desc_lo), "r"(a_desc_hi), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 ad, {%1, %2};\n\tmov.b64 bd, {%3, %4};\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %5, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_desc_lo), "r"(a_desc_hi), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-// barrier among `nthreads` threads (a multiple of 32) on hardware barrier `id` (1..15; 0 is __syncthreads)
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// register re-balancing between warpgroups (4 consecutive warps execute it together)
-template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-// one lane of a converged warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-// Arrive on `bar` (same offset in every CTA of the group) once all previously issued MMAs retire.
-template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  if constexpr (CG == 1) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-  } else {
-    const uint16_t mask = 3;
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(bar), "h"(mask)
-        : "memory");
-  }
-}
-template <int CG>
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  if constexpr (CG == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  } else {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-}
-template <int CG>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  if constexpr (CG == 1)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-  else
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptors (sm_100 format, version 1), split in 32-bit halves.
-// K-major, 128B swizzle: 8-row x 128-byte atoms, SBO (8-row group stride) = 1024 B, LBO unused.
-//   lo = start address >> 4 [0,14) | LBO >> 4 [16,30);  hi = SBO >> 4 [0,14) | version [14,16) | layout [29,32)
-constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
-// K-major, no swizzle: 8-row x 16-byte core matrices; SBO = 128 B between 8-row groups, LBO = byte
-// distance between the two 16-byte K chunks of one 16-element K step.
-constexpr uint32_t DESC_HI_NOSW = (128u >> 4) | (1u << 14);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes = 0) {
-  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-}
-// kind::f16 instruction descriptor: FP32 accum, BF16 x BF16, both K-major, M x N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------------------
 // kernel configuration
@@ -1057,40 +817,6 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static int get_encode_fn(EncodeTiledFn* out) {
-  static EncodeTiledFn cached = nullptr;
-  if (!cached) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CCVSQ_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    CCVSQ_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, CCVSQ_CUDA_ERROR,
-                  "cuTensorMapEncodeTiled entry point not available (driver too old?)");
-    cached = (EncodeTiledFn)fn;
-  }
-  *out = cached;
-  return CCVSQ_OK;
-}
-
-// codebook shadow: row-major [rows, D + 16] BF16; box = box_cols columns x box_rows rows
-static int make_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int64_t rows, int cols_total,
-                    int box_cols, int box_rows, CUtensorMapSwizzle swz) {
-  cuuint64_t gdim[2] = {(cuuint64_t)cols_total, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)cols_total * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CCVSQ_REQUIRE(r == CUDA_SUCCESS, CCVSQ_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d",
-                (int)r);
-  return CCVSQ_OK;
-}
-
 template <int CG, int BN>
 static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const float* e_max,
                          float tau, int K, int K_pad, int D, int n_cand, int nacc, int abuf,

@@ -34,6 +34,7 @@ _KERNELS_PER_CALL = {
     "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1, "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1,
     "ccvsq_finalize": 1, "ccvsq_ema_update": 2, "ccvsq_ema_update_packed": 2, "ccvsq_code_stats_fixed": 3,
     "ccvsq_gather_add": 1, "ccvsq_polyak": 1,
+    "ccvsq_encoder_tail_prepare": 1, "ccvsq_encoder_tail": 1,
     "ccvsq_quantize_forward": 0, "ccvsq_quantize_backward": 0,   # composites: counted by their wrappers
 }
 
@@ -566,3 +567,39 @@ def ema_update(weight: torch.Tensor, n_ema: torch.Tensor, sum_ema: torch.Tensor,
     scratch = torch.empty(1, dtype=torch.float32, device=weight.device)
     _call("ccvsq_ema_update", _ptr(weight), _ptr(n_ema), _ptr(sum_ema), _ptr(resid), _ptr(counts), K, D, float(decay),
                             float(eps), _ptr(scratch), _stream(weight.device))
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder tail: 1x1 EqualConv2d + bias + LeakyReLU (+ L2 normalisation) producing the latents
+# ------------------------------------------------------------------------------------------------
+def encoder_tail_supported(c_in: int, c_out: int) -> bool:
+    return c_in >= 64 and c_in % 64 == 0 and c_out >= 16 and c_out % 16 == 0 and (c_out <= 256 or c_out % 256 == 0)
+
+
+def encoder_tail_prepare(weight: torch.Tensor, scale: float) -> torch.Tensor:
+    """weight [C_out, C_in(,1,1)] fp32 -> the three BF16 terms of fl(weight * scale), [3, C_out, C_in]."""
+    w = _req(weight.detach().reshape(weight.shape[0], -1).contiguous(), torch.float32, "weight")
+    c_out, c_in = w.shape
+    terms = torch.empty(3, c_out, c_in, dtype=torch.bfloat16, device=w.device)
+    _call("ccvsq_encoder_tail_prepare", _ptr(w), c_out, c_in, float(scale), _ptr(terms), _stream(w.device))
+    return terms
+
+
+def encoder_tail(x: torch.Tensor, terms: torch.Tensor, bias: Optional[torch.Tensor], negative_slope: float = 0.1,
+                 normalize: bool = False) -> torch.Tensor:
+    """x [G, C_in, h, w] (or [G, C_in, S]) fp32 -> z of the same leading / spatial shape with C_out channels."""
+    _req(x, torch.float32, "x")
+    _, c_out, c_in = terms.shape
+    if x.shape[1] != c_in:
+        raise ValueError(f"x has {x.shape[1]} channels, the weight expects {c_in}")
+    G = x.shape[0]
+    S = x[0, 0].numel()
+    z = torch.empty((G, c_out) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return z
+    b = None if bias is None else _req(bias.detach(), torch.float32, "bias")
+    _call("ccvsq_encoder_tail", _ptr(x), G, c_in, S, _ptr(terms), _ptr(b), c_out, float(negative_slope), int(normalize), _ptr(z),
+          _stream(x.device))
+    if normalize:
+        PROFILER.launches += 1
+    return z

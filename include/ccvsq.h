@@ -237,6 +237,19 @@ int ccvsq_ema_update(float* E, float* n_ema, float* sum_ema, const float* resid,
 int ccvsq_ema_update_packed(float* E, float* n_ema, float* sum_ema, const float* packed, int K, int D,
                             float decay, float eps, float* scratch, void* stream);
 
+/* ---- encoder tail: the 1x1 convolution that produces the latents -------------------------
+ * Replaces the encoder's last block  ConvLayer(block_out, z_size, 1)  and the optional output normalisation
+ * (models/skip_vid_generator/models/skip_autoencoder.py:331,346-349; EqualConv2d :40-58; LeakyReLU(0.1) :98-99):
+ *     z[g, o, s] = lrelu_slope( sum_c fl(W[o, c] * scale) * x[g, c, s] + bias[o] ),   then z /= ||z||_2 over o if normalize
+ * on tcgen05 tensor cores with FP32-level accuracy: both operands are split into three BF16 terms and the six
+ * products above 2^-24 of the result are accumulated in FP32 ("BF16x6").
+ *   ccvsq_encoder_tail_prepare: W [C_out, C_in] fp32 -> W_terms [3, C_out, C_in] bf16 (once per weight version)
+ *   x [G, C_in, S] fp32 (NCHW, S = h*w), z [G, C_out, S] fp32 out; bias [C_out] (may be NULL)
+ * Requires C_in % 64 == 0, C_out % 16 == 0 and (C_out <= 256 or C_out % 256 == 0), 16-byte aligned pointers.        */
+int ccvsq_encoder_tail_prepare(const float* W, int C_out, int C_in, float scale, void* W_terms, void* stream);
+int ccvsq_encoder_tail(const float* x, int64_t G, int C_in, int S, const void* W_terms, const float* bias,
+                       int C_out, float negative_slope, int normalize, float* z, void* stream);
+
 /* ---- whole-op entry points ---------------------------------------------------------------------
  * ccvsq_quantize_forward enqueues the complete forward of the reference module
  * (quantize.py:32-74: flatten, nearest code, gather, loss, straight-through value, perplexity) with

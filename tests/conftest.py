@@ -16,7 +16,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+_ALL_NPZ = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+GOLDEN_NAMES = [n for n in _ALL_NPZ if not n.startswith("tail_")]        # quantizer fixtures (oracle/gen_golden.py)
+TAIL_NAMES = [n for n in _ALL_NPZ if n.startswith("tail_")]              # encoder-tail fixtures (oracle/gen_golden_tail.py)
 
 
 def pytest_configure(config):
@@ -63,3 +65,18 @@ class Golden:
 @pytest.fixture(params=GOLDEN_NAMES)
 def golden(request):
     return Golden(request.param)
+
+
+class TailGolden:
+    """One encoder-tail fixture produced by oracle/gen_golden_tail.py from the reference's own ConvLayer source."""
+
+    def __init__(self, name):
+        self.name = name
+        d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        t = lambda k: torch.from_numpy(d[k])
+        self.x, self.weight, self.bias, self.out, self.out_normalized = t("x"), t("weight"), t("bias"), t("out"), t("out_normalized")
+
+
+@pytest.fixture(params=TAIL_NAMES)
+def tail_golden(request):
+    return TailGolden(request.param)

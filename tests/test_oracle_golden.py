@@ -142,3 +142,14 @@ def test_oracle_empty_batch_matches_reference_behaviour():
     r = vq_oracle.forward(z, cb, 0.25)
     assert r.z_q.shape == z.shape and tuple(r.indices.shape) == (0, 1)
     assert torch.isnan(r.loss) and torch.isnan(r.perplexity)
+
+
+def test_oracle_encoder_tail_matches_reference_classes(tail_golden):
+    """The restated encoder tail (conv2d with weight * scale + bias, LeakyReLU(0.1), optional L2 normalisation) against
+    outputs of the reference's own EqualConv2d / ConvLayer source (oracle/gen_golden_tail.py)."""
+    g = tail_golden
+    out = vq_oracle.encoder_tail(g.x, g.weight, g.bias)
+    torch.testing.assert_close(out, g.out, rtol=1e-6, atol=1e-6)
+    out_n = vq_oracle.encoder_tail(g.x, g.weight, g.bias, normalize_out=True)
+    torch.testing.assert_close(out_n, g.out_normalized, rtol=1e-6, atol=1e-6)
+    assert float((out < 0).float().mean()) > 0.2          # the LeakyReLU branch is exercised
