@@ -761,6 +761,19 @@ def main():
         small = {"latents_per_call": int(zs.numel() // D), "layout": list(zs.shape), "K": K, "D": D,
                  "ms_per_call_eager": time_calls(eager), "ms_per_call_cuda_graph": time_calls(graphed.replay),
                  "note": "forward + embed_code; cuda_graph = VectorQuantizer.capture() replay (one driver call per step)"}
+        # the autoregressive sampler's per-frame step (quantized_video_model.py:939-964): decode gather -> [decoder +
+        # encoder trunk: a 1x1-conv stand-in] -> encoder tail -> quantizer, 16 latent frames of 8x8, one CUDA graph
+        from ccvs_b200 import EncoderTail
+        from ccvs_b200.reencode import ReencodeStep
+        cf = 512
+        tail_s = EncoderTail(cf, D).to(dev)
+        trunk = torch.nn.Sequential(torch.nn.Conv2d(D, cf, 1), torch.nn.Tanh()).to(dev)
+        code0 = torch.randint(0, K, (16, 64), device=dev)
+        stepper = ReencodeStep(vqs, tail_s, trunk, code0, (8, 8))
+        small["reencode_step"] = {"latents_per_call": 16 * 64, "ms_per_call_eager": time_calls(stepper.eager),
+                                  "ms_per_call_cuda_graph": time_calls(stepper.step),
+                                  "note": "ccvs_b200.reencode.ReencodeStep: embed_code (NCHW) -> stand-in trunk -> EncoderTail -> "
+                                          "encode_indices on a frozen codebook; graph = one driver call per generated frame"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -115,3 +115,30 @@ def test_encoder_tail_backward_and_errors():
     with pytest.raises(ValueError):
         EncoderTail(100, 64)                        # C_in not a multiple of 64
     assert not ops.encoder_tail_supported(64, 24 + 2)
+
+
+def test_reencode_step_graph_equals_eager_over_a_rollout():
+    """The autoregressive re-encode step (vid_step_decode, quantized_video_model.py:939-964) as one CUDA graph: same codes
+    as the eager chain over a rollout of several frames, and the decode half equals the oracle's embed_code."""
+    from ccvs_b200.reencode import ReencodeStep
+    gen = torch.Generator().manual_seed(9)
+    B, h, w, D, K, cf = 16, 8, 8, 256, 1024, 512
+    cb = torch.randn(K, D, generator=gen)
+    vq = VectorQuantizer(K, D, 0.25).to(DEV).eval()
+    tail = EncoderTail(cf, D).to(DEV)
+    trunk = torch.nn.Sequential(torch.nn.Conv2d(D, cf, 1), torch.nn.Tanh()).to(DEV)       # stand-in for decoder + encoder trunk
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+    code0 = torch.randint(0, K, (B, h * w), generator=gen).to(DEV)
+    stepper = ReencodeStep(vq, tail, trunk, code0, (h, w))
+    code = code0.clone()
+    for _ in range(4):
+        want = stepper.eager(code).clone()
+        got = stepper.step(code).clone()
+        assert torch.equal(got, want)
+        dec_ref = vq_oracle.embed_code(code.view(B, h, w).cpu(), cb).permute(0, 3, 1, 2)
+        assert torch.equal(stepper.decoded.cpu(), dec_ref)
+        assert int(got.min()) >= 0 and int(got.max()) < K
+        code = got
+    stepper.feed_back()
+    assert torch.equal(stepper.code, stepper.new_code)
