@@ -622,6 +622,24 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     const float emax = e_max ? __ldg(e_max) : 1.f;
     const float demax = e_max ? __ldg(e_max + 1) : 0.00390625f;
     uint32_t tl = 0, b = 0, b_phase = 0;
+    uint32_t ra[32], rb[32];                    // score chunks of the tile in flight (wide plan: both chunks of the half tile)
+    // wide plan: wait for the next accumulator, pull this group's 64 columns into registers, hand the accumulator back
+    auto load_half_tile = [&](uint32_t sweep, int j) {
+      mbar_wait(tmem_full(b), b_phase);
+      if (warp == 4) CCVSQ_TILE_STAMP(sweep, j, 3);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + (uint32_t)g * 64u;
+      tmem_ld32(taddr0, ra);
+      tmem_ld32(taddr0 + 32, rb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
+      }
+      if (warp == 4) CCVSQ_TILE_STAMP(sweep, j, 4);
+      if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
+    };
 
     for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
       const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
@@ -646,10 +664,12 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       for (uint32_t e = 0; e < CAP; ++e) pmax[e] = -FLT_MAX;
 
       for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(tmem_full(b), b_phase);
-        if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 3);
-        tc_fence_after();
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + (WIDE ? (uint32_t)g * 64u : 0u);
+        if constexpr (!WIDE) {
+          mbar_wait(tmem_full(b), b_phase);
+          if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 3);
+          tc_fence_after();
+        }
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;     // (narrow plans)
         const int col0 = j * BN + (WIDE ? g * 64 : 0);
         float peer_max = -FLT_MAX;              // wide plan: the other group's running maximum (a tile old at most)
         if constexpr (WIDE) peer_max = peer_running_max(tl);
@@ -700,19 +720,10 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           }
         };
 
-        uint32_t ra[32], rb[32];
         if constexpr (WIDE) {
           // both 32-column chunks of this group's half tile at once; the accumulator goes back to the MMA warp as
           // soon as they are in registers (the other group does the same with its half), the max trees run after
-          tmem_ld32(taddr0, ra);
-          tmem_ld32(taddr0 + 32, rb);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CG == 1) mbar_arrive(tmem_empty(b)); else mbar_arrive_cluster(te_bar + 8u * b);
-          }
-          if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 4);
+          load_half_tile(tl, j);
           process(ra, 0);
           process(rb, 32);
           asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(live_own), "r"(__float_as_uint(runmax)), "r"(tl) : "memory");   // (racy by design: any earlier value of THIS sweep is a valid lower bound)
@@ -736,10 +747,13 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           }
           if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 4);
           if constexpr (BN == 96) process(ra, 64); else process(rb, 32);
+          if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
         }
         if (warp == 4) CCVSQ_TILE_STAMP(tl, j, 5);
-        if (++b == (uint32_t)nacc) { b = 0; b_phase ^= 1; }
       }
+      // (Measured and dropped: reading tile 0 of the NEXT sweep into the free score registers here, before the end-of-sweep
+      //  work, so that its accumulator goes back to the MMA warp ~2 400 cycles earlier: c2 125.6 -> 147.5 us on the same
+      //  box, although the structure alone costs nothing — profiles/r02_screen_history.md.)
 
       if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == 4 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 7] = clock64(); }
       if (ablate & 1) continue;

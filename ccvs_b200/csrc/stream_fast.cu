@@ -429,13 +429,12 @@ __global__ void __launch_bounds__(FNT) rows4_kernel(const StreamArgs a, const in
 
 // Row-major, D % 128 == 0: one warp per RPW consecutive rows, lanes over the chunks of a row.  No
 // divisions or per-chunk index arithmetic: ~8 (gather) to ~25 (assign) instructions per 16 bytes.
-template <int MODE>
+template <int MODE, int RPW>
 __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kernel(const StreamArgs a, const int64_t N, const int D) {
   __shared__ float s_red[FNT / 32];
   __shared__ bool s_last;
   pdl_launch_dependents();
   pdl_wait();
-  constexpr int RPW = 4;
   const int lane = threadIdx.x & 31;
   const int Q = D >> 2, QL = D >> 7;                        // chunks per row / per lane
   const int64_t n_base = ((int64_t)blockIdx.x * (FNT / 32) + (threadIdx.x >> 5)) * RPW;
@@ -559,9 +558,16 @@ static int launch_cm4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
 template <int MODE>
 static int launch_rows4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
   if (L.D % 128 == 0) {
-    const int64_t blocks = (L.N + 4 * (FNT / 32) - 1) / (4 * (FNT / 32));
+    // rows per warp: 4 keeps the most loads in flight per lane; small inputs take 2 or 1 so that the grid still spans
+    // several waves of CTAs (at 4 rows per warp the Kinetics shard at D = 512 is 1.7 waves: the last one 0.7 full)
+    const int64_t slots = (int64_t)kNumSMs * 8;
+    int rpw = 4;
+    while (rpw > 1 && (L.N + rpw * (FNT / 32) - 1) / (rpw * (FNT / 32)) < 4 * slots) rpw >>= 1;
+    const int64_t blocks = (L.N + rpw * (FNT / 32) - 1) / (rpw * (FNT / 32));
     CCVSQ_REQUIRE(blocks < (1ll << 31), CCVSQ_BAD_SHAPE, "stream kernel: %lld CTAs exceed the grid limit", (long long)blocks);
-    CCVSQ_CUDA(launch_pdl(rowsw_kernel<MODE>, dim3((unsigned)blocks), dim3(FNT), 0, st, a, L.N, L.D));
+    if (rpw == 4) CCVSQ_CUDA(launch_pdl(rowsw_kernel<MODE, 4>, dim3((unsigned)blocks), dim3(FNT), 0, st, a, L.N, L.D));
+    else if (rpw == 2) CCVSQ_CUDA(launch_pdl(rowsw_kernel<MODE, 2>, dim3((unsigned)blocks), dim3(FNT), 0, st, a, L.N, L.D));
+    else CCVSQ_CUDA(launch_pdl(rowsw_kernel<MODE, 1>, dim3((unsigned)blocks), dim3(FNT), 0, st, a, L.N, L.D));
     CCVSQ_LAUNCH_CHECK();
     return CCVSQ_OK;
   }
