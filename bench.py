@@ -767,9 +767,21 @@ def main():
         from ccvs_b200.reencode import ReencodeStep
         cf = 512
         tail_s = EncoderTail(cf, D).to(dev)
-        trunk = torch.nn.Sequential(torch.nn.Conv2d(D, cf, 1), torch.nn.Tanh()).to(dev)
+        conv = torch.nn.Conv2d(D, cf, 1).to(dev)
+        feats0 = torch.randn(16, cf, 8, 8, device=dev)
+
+        def trunk(zdec):            # stand-in for decoder + encoder trunk: a 1x1 conv on the decoded latents + fixed diverse features
+            return feats0 + 1e-3 * torch.tanh(conv(zdec))
+
         code0 = torch.randint(0, K, (16, 64), device=dev)
-        stepper = ReencodeStep(vqs, tail_s, trunk, code0, (8, 8))
+        # a codebook that lies NEAR the latents this chain produces (a trained model's regime; against an unrelated random
+        # codebook every row is a near-tie and takes the exact fallback)
+        vqr = _VQ(K, D, 0.25).to(dev).eval()
+        with torch.no_grad():
+            rows = tail_s(feats0).permute(0, 2, 3, 1).reshape(-1, D)
+            pick = rows[torch.randperm(rows.shape[0], device=dev)[:K]]
+            vqr.embedding.weight.copy_(pick + 0.02 * rows.std() * torch.randn_like(pick))
+        stepper = ReencodeStep(vqr, tail_s, trunk, code0, (8, 8))
         small["reencode_step"] = {"latents_per_call": 16 * 64, "ms_per_call_eager": time_calls(stepper.eager),
                                   "ms_per_call_cuda_graph": time_calls(stepper.step),
                                   "note": "ccvs_b200.reencode.ReencodeStep: embed_code (NCHW) -> stand-in trunk -> EncoderTail -> "
