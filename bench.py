@@ -297,20 +297,25 @@ def encoder_tail_record(dev, peaks_):
 
 def train_record(args, dev, world, cb, z, barrier):
     """Training-mode quantizer (BASELINE configs[4]) at the c2 shape on every rank: forward + straight-through backward
-    + commitment loss + EMA codebook update with ONE NCCL all-reduce of the packed code statistics per step.  Three
-    variants, same steps: all-reduce overlapped with the backward (the product default), all-reduce serial in
-    front of the backward, and no all-reduce at all (sync off) -> how much of the collective is exposed."""
+    + commitment loss + EMA codebook update, the code statistics exchanged between the ranks once per step.  Variants,
+    same steps: `graphed` = the whole step as one CUDA graph with the NVLink peer exchange fused into the EMA update
+    (the product path on one node); `peer` = the same exchange issued eagerly; `nccl_overlapped` / `nccl_serial` = one
+    NCCL all-reduce of the packed statistics under / in front of the backward; `no_exchange` = sync off -> how much of
+    the collective is exposed, and how much of the step is host issue time."""
     import torch.distributed as dist
-    from ccvs_b200.quantize import EMAVectorQuantizer
+    from ccvs_b200.quantize import EMAVectorQuantizer, GraphedTrainStep
     K, D = cb.shape
     n_lat = z.numel() // D
     cb = cb.clone()                        # (replicated codebook: make_inputs draws it from the same seed on every rank)
     g_out = torch.randn_like(z)
     zt = z.detach().clone().requires_grad_(True)
-    res = {}
-    for name, kw in (("overlapped", dict(sync=True, overlap=True)), ("serial", dict(sync=True, overlap=False)),
-                     ("no_allreduce", dict(sync=False))):
-        if world == 1 and name != "no_allreduce":
+    res, notes = {}, {}
+    variants = [("graphed", dict(sync=True, overlap=True), True), ("peer", dict(sync=True, overlap=True, exchange="auto"), False),
+                ("nccl_overlapped", dict(sync=True, overlap=True, exchange="nccl"), False),
+                ("nccl_serial", dict(sync=True, overlap=False, exchange="nccl"), False),
+                ("no_exchange", dict(sync=False), False), ("no_exchange_graphed", dict(sync=False), True)]
+    for name, kw, graphed in variants:
+        if world == 1 and name not in ("no_exchange", "no_exchange_graphed"):
             continue
         vq = EMAVectorQuantizer(K, D, 0.25, decay=0.99, search_mode=args.search_mode, **kw).to(dev).train()
         with torch.no_grad():
@@ -323,9 +328,20 @@ def train_record(args, dev, world, cb, z, barrier):
             z_q, loss, _ = vq(zt)
             torch.autograd.backward([z_q, loss], [g_out, torch.ones_like(loss)])
 
-        for _ in range(max(3, args.warmup)):
-            tstep()
-        vq.sync_codebook()
+        try:
+            if graphed:
+                gs = GraphedTrainStep(vq, zt.detach(), g_out, warmup=max(3, args.warmup))
+                tstep = gs.replay                                                            # noqa: F811
+            else:
+                for _ in range(max(3, args.warmup)):
+                    tstep()
+                vq.sync_codebook()
+        except RuntimeError as e:      # (no peer access on this box: the NCCL variants still run; every rank takes this branch)
+            notes[name] = str(e)[:160]
+            del vq
+            continue
+        if name == "peer" and vq._peer is None:
+            notes[name] = "peer exchange unavailable: NCCL was used"
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -338,22 +354,34 @@ def train_record(args, dev, world, cb, z, barrier):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res[name] = float(t)
-        if world > 1 and name == "overlapped":      # every rank must hold the same codebook after the same steps
+        if world > 1 and name in ("graphed", "peer", "nccl_overlapped"):   # every rank must hold the same codebook after the same steps
             w = vq.embedding.weight.detach()
             lo, hi = w.clone(), w.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-            res["codebooks_identical_across_ranks"] = bool(torch.equal(lo, hi))
+            res["codebooks_identical_across_ranks_" + name] = bool(torch.equal(lo, hi)) and bool(torch.isfinite(w).all())
         del vq
-    main = res.get("overlapped", res["no_allreduce"])
+    order = ("graphed", "peer", "nccl_overlapped") if world > 1 else ("no_exchange_graphed", "no_exchange")
+    main_name = next(n for n in order if n in res)
+    main = res[main_name]
     rec = {"workload": "training-mode quantizer at the c2 shape per GPU: fwd + STE backward (dz) + loss + EMA codebook update",
-           "ms_per_step": main, "value": n_lat * world / (main * 1e-3), "unit": UNIT, "n_gpus": world,
-           "ms_per_step_by_variant": res, "allreduce_bytes": (K * D + K) * 4 if world > 1 else 0,
-           "collective": "one NCCL all-reduce (SUM, FP32) of [resid K*D | counts K] per step, issued async after the forward, "
-                         "waited for at the end of the quantizer's backward" if world > 1 else "none (one rank)"}
-    if world > 1:
-        rec["exposed_allreduce_us"] = (res["overlapped"] - res["no_allreduce"]) * 1e3
-        rec["exposed_allreduce_us_if_serial"] = (res["serial"] - res["no_allreduce"]) * 1e3
+           "ms_per_step": main, "variant": main_name, "value": n_lat * world / (main * 1e-3), "unit": UNIT, "n_gpus": world,
+           "ms_per_step_by_variant": res, "exchange_bytes_per_rank": (K * D + K) * 4 if world > 1 else 0,
+           "collective": ("NVLink peer exchange: every rank pushes its packed statistics [resid K*D | counts K] into an inbox on "
+                          "every peer after its forward; the EMA update kernel waits for the flags, sums the inboxes in rank "
+                          "order and rewrites the codebook (csrc/peer_exchange.cu); whole step = one CUDA graph"
+                          if main_name == "graphed" else
+                          "NVLink peer exchange fused into the EMA update (eager launches)" if main_name == "peer" else
+                          "one NCCL all-reduce (SUM, FP32) of [resid K*D | counts K] per step, issued async after the forward, "
+                          "waited for at the end of the quantizer's backward" if world > 1 else "none (one rank)")}
+    if notes:
+        rec["notes"] = notes
+    if world > 1 and "no_exchange_graphed" in res and "graphed" in res:
+        rec["exposed_exchange_us"] = (res["graphed"] - res["no_exchange_graphed"]) * 1e3
+    if world > 1 and "no_exchange" in res:
+        for n in ("peer", "nccl_overlapped", "nccl_serial"):
+            if n in res:
+                rec["exposed_exchange_us_" + n] = (res[n] - res["no_exchange"]) * 1e3
     return rec
 
 

@@ -87,6 +87,13 @@ SIGNATURES = {
     "ccvsq_finalize": (c_int, [_P, _P, _P, _P, c_int, c_int, c_double, c_double, c_float, _P, _P, _P, _P]),
     "ccvsq_ema_update": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
     "ccvsq_ema_update_packed": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
+    "ccvsq_peer_exchange_bytes": (c_uint64, [c_int, c_int, c_int]),
+    "ccvsq_peer_alloc": (c_int, [c_uint64, POINTER(c_void_p), _P]),
+    "ccvsq_peer_open": (c_int, [_P, POINTER(c_void_p)]),
+    "ccvsq_peer_close": (c_int, [_P]),
+    "ccvsq_peer_free": (c_int, [_P]),
+    "ccvsq_peer_publish": (c_int, [_P, c_int, c_int, POINTER(c_void_p), c_int, c_int, _P]),
+    "ccvsq_peer_ema_update": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, _P]),
     "ccvsq_encoder_tail_prepare": (c_int, [_P, c_int, c_int, c_float, _P, _P]),
     "ccvsq_encoder_tail": (c_int, [_P, c_int64, c_int, c_int, _P, _P, c_int, c_float, c_int, _P, _P]),
     "ccvsq_gather_add": (c_int, [_P, _P, c_int, c_int, c_int64, _P, c_int64, _P, _P, _P]),

@@ -33,7 +33,7 @@ _KERNELS_PER_CALL = {
     "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_trace": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
     "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1, "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1,
     "ccvsq_finalize": 1, "ccvsq_ema_update": 2, "ccvsq_ema_update_packed": 2, "ccvsq_code_stats_fixed": 3,
-    "ccvsq_gather_add": 1, "ccvsq_polyak": 1,
+    "ccvsq_gather_add": 1, "ccvsq_polyak": 1, "ccvsq_peer_publish": 1, "ccvsq_peer_ema_update": 2,
     "ccvsq_encoder_tail_prepare": 1, "ccvsq_encoder_tail": 1,
     "ccvsq_quantize_forward": 0, "ccvsq_quantize_backward": 0,   # composites: counted by their wrappers
 }

@@ -524,6 +524,62 @@ class GraphedQuantizer:
         return self.replay()
 
 
+class GraphedTrainStep:
+    """One CUDA graph for a whole TRAINING step of the quantizer on fixed-shape inputs: forward (search, assign, loss,
+    perplexity, code statistics), the statistics exchange, the straight-through backward (dz, and dE for a codebook that
+    takes gradients) and — for `EMAVectorQuantizer` — the EMA codebook update.
+
+    Why: at the reference's batch sizes, and on 8 ranks sharing one host, the training step is bound by host issue time
+    (0.3-0.5 ms of Python / autograd / launch overhead against 0.45 ms of kernels at the BASELINE c2 shape); the graph
+    replays all of it with one driver call.  The caller writes new latents into `z_static` and the upstream gradient of
+    z_q into `grad_zq_static`, calls `replay()`, and reads the static outputs.  With several ranks the exchange must be
+    the NVLink peer exchange (its step counter lives in device memory; an NCCL collective is not captured here).
+    Construct on every rank at the same point: the warm-up steps run the exchange for real."""
+
+    def __init__(self, vq: "VectorQuantizer", z_static: torch.Tensor, grad_zq_static: torch.Tensor,
+                 grad_loss: float = 1.0, warmup: int = 3):
+        if not z_static.is_cuda:
+            raise RuntimeError("CUDA only; there is no CPU fallback")
+        if not vq.training:
+            raise RuntimeError("GraphedTrainStep captures a training step: call vq.train() first")
+        self.vq = vq
+        self.z = z_static.detach().requires_grad_(True)
+        self.grad_zq = grad_zq_static
+        dev = z_static.device
+        g_loss = self.grad_loss = torch.full((), float(grad_loss), dtype=torch.float32, device=dev)   # (static: the graph reads it)
+        w = vq.embedding.weight
+
+        def step():
+            self.z.grad = None
+            if w.requires_grad:
+                w.grad = None
+            z_q, loss, (perp, _, idx) = vq(self.z)
+            torch.autograd.backward([z_q, loss], [self.grad_zq, g_loss])
+            if hasattr(vq, "sync_codebook"):
+                vq.sync_codebook()
+            return z_q, loss, perp, idx
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        if getattr(vq, "sync", False) and vq_dist.world_info()[1] > 1 and getattr(vq, "_peer", None) is None:
+            raise RuntimeError("GraphedTrainStep with several ranks needs the NVLink peer exchange (exchange='auto' / 'peer' "
+                               "on one node); this module exchanges through NCCL")
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.z_q, self.loss, self.perplexity, self.indices = step()
+        self.dz = self.z.grad
+        self.dE = w.grad if w.requires_grad else None
+
+    def replay(self):
+        self.graph.replay()
+        return self.z_q, self.loss, self.perplexity, self.indices, self.dz
+
+
 class EMAVectorQuantizer(VectorQuantizer):
     """EXTENSION (not in the reference): codebook trained by exponential-moving-average statistics
     instead of the reference's Adam-on-codebook-loss (`--q_use_ema` in the reference is a
@@ -536,12 +592,20 @@ class EMAVectorQuantizer(VectorQuantizer):
     """
 
     def __init__(self, n_e, e_dim, beta, mult=1, *, decay: float = 0.99, eps: float = 1e-5, sync: bool = True,
-                 overlap: bool = True, **kw):
+                 overlap: bool = True, exchange: str = "auto", **kw):
         super().__init__(n_e, e_dim, beta, mult=mult, normalize=False, **kw)
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError(f"exchange must be 'auto', 'peer' or 'nccl'; got {exchange!r}")
         self.decay = decay
         self.eps = eps
         self.sync = sync
-        self.overlap = overlap            # hide the statistics all-reduce under the backward pass (see forward)
+        self.overlap = overlap            # hide the statistics exchange under the backward pass (see forward)
+        # how the ranks exchange the statistics: 'peer' = pushed into every rank's inbox over NVLink and summed by the EMA
+        # update kernel itself (ccvs_b200.peer, one node); 'nccl' = one all-reduce of the packed buffer; 'auto' = peer
+        # when every rank can map every other rank's memory, else nccl (decided once, collectively, at the first step)
+        self.exchange = exchange
+        self._peer = None
+        self._peer_decided = False
         self.embedding.weight.requires_grad_(False)
         self._inplace_codebook_update = True
         self._last_resid = None
@@ -588,11 +652,31 @@ class EMAVectorQuantizer(VectorQuantizer):
                 if not (self.sync and vq_dist.world_info()[1] > 1):
                     return out                 # nothing was assigned: the codebook keeps its state
                 buf.zero_()                    # an empty shard still joins the collective, with zero statistics
-            work = vq_dist.start_reduce_ema_stats(buf, None, self.n_e, self.e_dim) if self.sync else None
+            work = None
+            if self.sync and vq_dist.world_info()[1] > 1:
+                peer = self._peer_exchange(z.device)
+                if peer is not None:
+                    peer.publish(buf, overlap=self.overlap)   # posted NVLink writes into every rank's inbox; nobody waits here
+                    work = peer
+                else:
+                    work = vq_dist.start_reduce_ema_stats(buf, None, self.n_e, self.e_dim)
             self._pending = (work, buf)
             if not will_defer:
                 self.sync_codebook()
         return out
+
+    def _peer_exchange(self, device):
+        """The NVLink peer exchange of this module, set up (collectively) at the first multi-rank training step; None when
+        the ranks exchange through NCCL."""
+        if not self._peer_decided:
+            from .peer import PeerExchange
+            self._peer_decided = True
+            if self.exchange != "nccl":
+                self._peer = PeerExchange.create(self.n_e, self.e_dim, device)
+                if self._peer is None and self.exchange == "peer":
+                    raise RuntimeError("exchange='peer': the ranks cannot map each other's memory (one node, one process per "
+                                       "GPU, peer access and CUDA IPC are required)")
+        return self._peer
 
     def _begin_deferred(self):
         """Token of a forward that keeps the LIVE codebook for its backward (deferred mode), else None."""
@@ -621,6 +705,10 @@ class EMAVectorQuantizer(VectorQuantizer):
         if self._outstanding is not None:
             self._stale_codebooks[self._outstanding] = self.embedding.weight.detach().clone()
             self._outstanding = None
+        if work is not None and work is self._peer:
+            # collective + update in one pass: wait for the ranks' pushes, sum the inbox slots in rank order, EMA update
+            work.ema_update(self.embedding.weight, self.ema_count, self.ema_sum, self.decay, self.eps)
+            return
         if work is not None:
             work.wait()            # the current STREAM waits for the collective (no host block with NCCL)
         ops.ema_update_packed(self.embedding.weight, self.ema_count, self.ema_sum, buf, self.decay, self.eps)

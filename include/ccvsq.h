@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CCVSQ_VERSION 201 /* major*100 + minor; 2.x: ccvsq_forward_args starts with struct_size */
+#define CCVSQ_VERSION 202 /* major*100 + minor; 2.x: ccvsq_forward_args starts with struct_size; 2.02: ccvsq_peer_* */
 
 typedef enum ccvsq_status {
   CCVSQ_OK = 0,
@@ -236,6 +236,29 @@ int ccvsq_ema_update(float* E, float* n_ema, float* sum_ema, const float* resid,
  * all-reduce sums over the ranks; ccvsq_forward_args.resid / .counts_f32 fill it in the forward): no unpacking step. */
 int ccvsq_ema_update_packed(float* E, float* n_ema, float* sum_ema, const float* packed, int K, int D,
                             float decay, float eps, float* scratch, void* stream);
+
+/* ---- training collective over NVLink peer memory (EMA extension; replaces the all-reduce of the packed buffer) --------
+ * The reference exchanges training state between ranks with NCCL through DDP / apex (tools/engine.py:71-74,127-132).
+ * For the EMA statistics [resid: K*D | counts: K] — 1 MB, pure latency for a ring — every rank instead PUSHES its
+ * buffer into an inbox slot on every peer (ccvsq_peer_publish, right after the forward; posted NVLink writes + one
+ * system-scope flag per peer), and ccvsq_peer_ema_update waits for the W flags, sums the W local slots in rank order
+ * (bit-identical on every rank) and applies the EMA update of ccvsq_ema_update in the same pass.  The step counter and
+ * the double-buffer parity live in the exchange area, so both calls can be captured in a CUDA graph.
+ *   area      ccvsq_peer_exchange_bytes(K, D, world) bytes from ccvsq_peer_alloc (cudaMalloc + cudaIpcGetMemHandle,
+ *             zero-filled); the 64-byte handle goes to the other ranks (any transport), which map it with
+ *             ccvsq_peer_open.  areas[r] = rank r's area as addressable from THIS process (areas[rank] = own).
+ *   Every rank calls publish then update exactly once per step, in that order, on one stream.  A rank that never
+ *   publishes makes the others trap after ~60 s (no silent hang, no partial sums).  One process per GPU, one node. */
+#define CCVSQ_PEER_MAX_WORLD 16
+#define CCVSQ_PEER_HANDLE_BYTES 64
+uint64_t ccvsq_peer_exchange_bytes(int K, int D, int world);
+int ccvsq_peer_alloc(uint64_t bytes, void** ptr, void* handle64);
+int ccvsq_peer_open(const void* handle64, void** ptr);
+int ccvsq_peer_close(void* ptr);
+int ccvsq_peer_free(void* ptr);
+int ccvsq_peer_publish(const float* stats, int K, int D, void* const* areas, int rank, int world, void* stream);
+int ccvsq_peer_ema_update(float* E, float* n_ema, float* sum_ema, void* area, int K, int D, int world,
+                          float decay, float eps, void* stream);
 
 /* ---- encoder tail: the 1x1 convolution that produces the latents -------------------------
  * Replaces the encoder's last block  ConvLayer(block_out, z_size, 1)  and the optional output normalisation

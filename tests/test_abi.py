@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 
 def test_version():
-    assert _lib.load().ccvsq_version() == 201
+    assert _lib.load().ccvsq_version() == 202
 
 
 def test_argument_validation_without_gpu():

@@ -56,7 +56,7 @@ def _init(rank, world, port):
 SHAPE, K, D, STEPS = (8, 256, 16, 16), 1024, 256, 3
 
 
-def _ema_worker(rank, world, port, q, overlap):
+def _ema_worker(rank, world, port, q, overlap, exchange="nccl", graphed=False):
     dist = _init(rank, world, port)
     import vq_oracle
     from ccvs_b200.quantize import EMAVectorQuantizer
@@ -66,31 +66,48 @@ def _ema_worker(rank, world, port, q, overlap):
     per = SHAPE[0] // world
     z = z_all[rank * per:(rank + 1) * per].to(dev).requires_grad_(True)
     g = g_all[rank * per:(rank + 1) * per].to(dev)
-    vq = EMAVectorQuantizer(K, D, 0.25, decay=0.9, sync=True, overlap=overlap).to(dev).train()
-    with torch.no_grad():
-        vq.embedding.weight.copy_(cb.to(dev))
-        vq.ema_sum.copy_(cb.to(dev))
-        vq.ema_count.fill_(1.0)
+    vq = EMAVectorQuantizer(K, D, 0.25, decay=0.9, sync=True, overlap=overlap, exchange=exchange).to(dev).train()
+
+    def reset():
+        with torch.no_grad():
+            vq.sync_codebook()
+            vq.embedding.weight.copy_(cb.to(dev))
+            vq.ema_sum.copy_(cb.to(dev))
+            vq.ema_count.fill_(1.0)
+
+    reset()
     grads = []
-    for _ in range(STEPS):
-        z.grad = None
-        z_q, loss, _ = vq(z)
-        torch.autograd.backward([z_q, loss], [g, torch.ones_like(loss)])
-        grads.append(z.grad.detach().cpu().clone())
-    vq.sync_codebook()
+    if graphed:
+        from ccvs_b200.quantize import GraphedTrainStep
+        gs = GraphedTrainStep(vq, z.detach().clone(), g.clone(), warmup=3)   # (its warm-up steps move the codebook:
+        assert vq._peer is not None and vq._peer.steps >= 3                  #  start again from the initial state)
+        reset()
+        for _ in range(STEPS):
+            gs.replay()
+            grads.append(gs.dz.detach().cpu().clone())
+    else:
+        for _ in range(STEPS):
+            z.grad = None
+            z_q, loss, _ = vq(z)
+            torch.autograd.backward([z_q, loss], [g, torch.ones_like(loss)])
+            grads.append(z.grad.detach().cpu().clone())
+        vq.sync_codebook()
+    assert (vq._peer is not None) == (exchange == "peer")
     torch.cuda.synchronize()
     q.put((rank, vq.embedding.weight.detach().cpu(), vq.ema_count.cpu(), vq.ema_sum.cpu(), torch.stack(grads)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [True, False])
-def test_ema_training_two_ranks_equal_one_gpu_on_the_whole_batch(overlap):
-    """The training collective: after the same steps every rank holds the SAME codebook / EMA state (bit for bit —
-    they apply the same all-reduced statistics), and it equals the single-GPU run on the concatenated batch up to
-    the summation order of the FP32 statistics."""
+@pytest.mark.parametrize("overlap,exchange,graphed", [(True, "nccl", False), (False, "nccl", False), (True, "peer", False),
+                                                      (False, "peer", False), (True, "peer", True)])
+def test_ema_training_two_ranks_equal_one_gpu_on_the_whole_batch(overlap, exchange, graphed):
+    """The training collective — NCCL all-reduce of the packed statistics, or the NVLink peer exchange fused into the EMA
+    update (eager and replayed from one CUDA graph per step): after the same steps every rank holds the SAME codebook /
+    EMA state (bit for bit — they apply the same summed statistics), and it equals the single-GPU run on the
+    concatenated batch up to the summation order of the FP32 statistics."""
     _need_two_gpus()
-    got = _spawn(_ema_worker, 2, overlap)
+    got = _spawn(_ema_worker, 2, overlap, exchange, graphed)
     (_, w0, n0, s0, dz0), (_, w1, n1, s1, dz1) = got
     assert torch.equal(w0, w1) and torch.equal(n0, n1) and torch.equal(s0, s1)
 
