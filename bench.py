@@ -239,12 +239,19 @@ def k16384_records(dev, search_mode: str, peaks_):
                                          ops._ptr(hdr), ops._stream(dev)))
         t_rows = med(lambda: ops._call("ccvsq_gather", ops._ptr(idx), ops._ptr(cb), K, rl, ops._ptr(dec), ops._ptr(err), ops._stream(dev)))
         t_cm = med(lambda: ops._call("ccvsq_gather", ops._ptr(idx), ops._ptr(cb), K, lay, ops._ptr(dec), ops._ptr(err), ops._stream(dev)))
+        # measuring sticks at the same size: a device copy moves assign's bytes (read 4D + write 4D per latent), a device fill
+        # writes the decode's bytes — at c3d512 the whole working set (134 MB) is about the size of L2 and a launch is ~30 us,
+        # so neither reaches the large-copy peak the fractions below are quoted against
+        t_copy = med(lambda: zq.copy_(z))
+        t_fill = med(lambda: dec.zero_())
         gb = lambda bytes_, ms: bytes_ / (ms * 1e-3) / 1e9
         hbm[wl] = {
             "layout": [clips, frames, D, h, w], "K": K,
             "assign": {"GBs": gb(n * (8 * D + 8), t_assign), "frac_of_hbm_peak": gb(n * (8 * D + 8), t_assign) / hbm_peak, "ms": t_assign},
             "decode_gather": {"GBs": gb(n * (4 * D + 8), t_rows), "frac_of_hbm_peak": gb(n * (4 * D + 8), t_rows) / hbm_peak, "ms": t_rows},
             "decode_gather_channel_major": {"GBs": gb(n * (4 * D + 8), t_cm), "frac_of_hbm_peak": gb(n * (4 * D + 8), t_cm) / hbm_peak, "ms": t_cm},
+            "device_copy_of_assign_bytes_ms": t_copy, "assign_vs_device_copy": t_copy / t_assign,
+            "device_fill_of_decode_bytes_ms": t_fill, "decode_gather_vs_device_fill": t_fill / t_rows,
         }
         del z, cb, pcb, o, idx, zq, dec
         torch.cuda.empty_cache()

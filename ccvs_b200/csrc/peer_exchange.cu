@@ -38,8 +38,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // every rank's statistics into every peer's inbox (own slot included), then the flags
@@ -67,15 +67,18 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(const float* __restri
   }
   __threadfence_system();
   __syncthreads();
+  __shared__ uint32_t s_last;
   if (threadIdx.x == 0) {
     const uint32_t t = atomicAdd(hdr + HDR_TICKET_PUB, 1u);
-    if (t == gridDim.x - 1) {          // all CTAs of this grid have written and fenced
+    s_last = t == gridDim.x - 1 ? 1u : 0u;
+    if (s_last) {                      // all CTAs of this grid have written and fenced
       hdr[HDR_TICKET_PUB] = 0;
-      __threadfence_system();
-      for (int p = 0; p < world; ++p)
-        st_release_sys(reinterpret_cast<uint32_t*>(peers.p[p]) + HDR_FLAGS + parity * PEER_MAX_WORLD + rank, seq + 1u);
-    }
+      __threadfence_system();          // ONE system-scope fence, then the W flags in parallel (a release store per peer would
+    }                                  // serialise W NVLink round trips: the last peer would see its flag ~15 us late)
   }
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < world)
+    st_relaxed_sys(reinterpret_cast<uint32_t*>(peers.p[threadIdx.x]) + HDR_FLAGS + parity * PEER_MAX_WORLD + rank, seq + 1u);
 }
 
 // wait (bounded) until every rank's statistics of this step have landed in the local inbox

@@ -64,7 +64,8 @@ constexpr int BM = 128;              // latent rows per CTA (TMEM lanes)
 constexpr uint32_t ENTRY_BYTES = 8 * BM * 16 + BM * 8;
 constexpr uint32_t HDR_OFFSET = 8 * BM * 16;
 // entries per row and epilogue group (the same shared memory per row for the one-group and the two-group plans)
-__host__ __device__ constexpr int park_cap(int bn) { return bn == 128 ? 3 : 6; }
+// (the plan with the second A buffer in shared memory gives one entry per group back: 64 KiB of staging)
+__host__ __device__ constexpr int park_cap(int bn, bool a_smem = false) { return bn == 128 ? (a_smem ? 2 : 3) : 6; }
 constexpr int MAX_SLOTS = 16;
 // tensor-memory columns (32-bit):
 //   BN < 128 : [0, nacc*BN) accumulators | [nacc*BN, +8) bias-extension A block | then abuf_n A buffers of D/2
@@ -83,11 +84,11 @@ struct ScreenCfg {
 __host__ __device__ constexpr int screen_threads(int bn) { return bn == 128 ? 640 : 512; }
 
 struct ScreenSmem {
-  uint32_t slots, list, norm, epst, cblk, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
+  uint32_t slots, astage, list, norm, epst, cblk, bars, total;   // byte offsets inside the 1024-aligned dynamic smem
   uint32_t block_bytes, ext_off, slot_bytes, slot_tx;
   int nslots;
 };
-__host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg, int bn) {
+__host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg, int bn, bool a_smem = false) {
   ScreenSmem s;
   const uint32_t nepg = bn == 128 ? 2 : 1;
   const uint32_t rows = bn / cg;                    // codes of a tile held by one CTA
@@ -97,12 +98,16 @@ __host__ __device__ inline ScreenSmem screen_smem_layout(int dblk, int cg, int b
   s.slot_bytes = (s.slot_tx + 1023u) & ~1023u;
   const uint32_t norm_bytes = 2 * 2 * 2 * BM * 4 + 2 * BM * 8;   // [A buffer][loader half][||z||^2, ||z - bf16(z)||^2][row] | [group][row] {live running max, sweep}
   const uint32_t cblk_bytes = bn == 128 ? BM * 32 : 0;
-  const uint32_t list_bytes = (uint32_t)park_cap(bn) * ENTRY_BYTES;      // per epilogue group
-  const uint32_t fixed = nepg * list_bytes + norm_bytes + nepg * BM * 16 + cblk_bytes + 512;
+  const uint32_t list_bytes = (uint32_t)park_cap(bn, a_smem) * ENTRY_BYTES;      // per epilogue group
+  // second A buffer (BF16, K-major without swizzle: 16-byte chunk kc of row r at kc * BM*16 + r*16) of the plan that
+  // alternates the A operand between tensor memory and shared memory
+  const uint32_t astage_bytes = a_smem ? (uint32_t)dblk * 64u * 2u * BM : 0u;
+  const uint32_t fixed = nepg * list_bytes + norm_bytes + nepg * BM * 16 + cblk_bytes + 512 + astage_bytes;
   int n = (int)((227u * 1024u - fixed) / s.slot_bytes);
   s.nslots = n > MAX_SLOTS ? MAX_SLOTS : n;
   uint32_t off = 0;
   s.slots = off; off += (uint32_t)s.nslots * s.slot_bytes;
+  s.astage = off; off += astage_bytes;
   s.list = off;  off += nepg * list_bytes;          // per epilogue group: park_cap entries (see ENTRY_BYTES)
   s.norm = off;  off += norm_bytes;
   s.epst = off;  off += nepg * BM * 16;             // [group][row] {running max, best code, codes inside the margin, entries}: end-of-sweep exchange
@@ -323,7 +328,7 @@ __device__ __forceinline__ void pack_chunk(const float (&v)[32], uint32_t (&pk)[
     }                                                                                                              \
   } while (0)
 
-template <int CG, bool DBG, int BN>
+template <int CG, bool DBG, int BN, bool ASM>
 __global__ void __launch_bounds__(screen_threads(BN), 1)
 screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_ext,
               const float* __restrict__ z, const Lay L, const float* __restrict__ e_max, float tau,
@@ -342,7 +347,8 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
   constexpr bool WIDE = Cfg::WIDE;
   constexpr int NEPG = Cfg::NEPG;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const ScreenSmem lay = screen_smem_layout(dblk, CG, BN);
+  static_assert(!ASM || BN == 128, "the shared-memory A buffer belongs to the wide-tile plan");
+  const ScreenSmem lay = screen_smem_layout(dblk, CG, BN, ASM);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -467,7 +473,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       uint32_t phase = 0, tl = 0, b = 0, b_phase = 0;
       for (int gt = group; gt < num_group_tiles; gt += num_groups, ++tl) {
         const uint32_t ab = tl % abuf_n, a_phase = (tl / abuf_n) & 1;
-        const uint32_t a_tmem = tmem_base + TM_A + ab * a_cols;
+        const uint32_t a_tmem = tmem_base + TM_A + (ASM ? 0u : ab * a_cols);
         for (int j = 0; j < n_tiles; ++j) {
           if (j == 0) { if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 0] = clock64(); } }
           mbar_wait(tmem_empty(b), b_phase ^ 1);
@@ -489,13 +495,26 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
             else
               umma_ts<CG>(d_tmem, tmem_base + TM_EXT, desc_lo(sbase + lay.ext_off, ROWS * 16), DESC_HI_NOSW, idesc, 0u);
             uint32_t lo = desc_lo(sbase);
-            uint32_t a_addr = a_tmem;
-            for (int kb = 0; kb < dblk; ++kb) {
+            if (ASM && ab == 1) {
+              // odd row tiles: A from the shared-memory buffer (SS form), one 16-element K step = two 16-byte chunks
+              // BM*16 bytes apart
+              uint32_t alo = desc_lo(smem_base + lay.astage, BM * 16);
+              for (int kb = 0; kb < dblk; ++kb) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_ts<CG>(d_tmem, a_addr + k * 8, lo + k * 2, DESC_HI_SW128, idesc, 1u);
-              lo += lay.block_bytes >> 4;
-              a_addr += 32;
+                for (int k = 0; k < 4; ++k)
+                  umma_ss<CG>(d_tmem, alo + k * ((2 * BM * 16) >> 4), DESC_HI_NOSW, lo + k * 2, DESC_HI_SW128, idesc, 1u);
+                lo += lay.block_bytes >> 4;
+                alo += (8 * BM * 16) >> 4;
+              }
+            } else {
+              uint32_t a_addr = a_tmem;
+              for (int kb = 0; kb < dblk; ++kb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_ts<CG>(d_tmem, a_addr + k * 8, lo + k * 2, DESC_HI_SW128, idesc, 1u);
+                lo += lay.block_bytes >> 4;
+                a_addr += 32;
+              }
             }
             umma_commit<CG>(empty_bar(slot));      // B slot reusable once these MMAs retire
             umma_commit<CG>(tmem_full(b));         // accumulator tile complete
@@ -569,22 +588,37 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == Cfg::LD_WARP0 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 4] = clock64(); }
       tc_fence_after();
       float ss = 0.f, dd = 0.f;                 // ||z||^2 and ||z - bf16(z)||^2 of this half row (screening margin)
-      const uint32_t dst = lane_base + ab * a_cols;
+      const uint32_t dst = lane_base + (ASM ? 0u : ab * a_cols);
+      const bool to_smem = ASM && ab == 1;
+      // shared-memory A buffer: chunk kc (8 dims, 16 bytes) of row r at kc * BM*16 + r*16 — a warp's store of one
+      // chunk is 512 contiguous bytes
+      const uint32_t sdst = smem_base + lay.astage + (uint32_t)(h * (half / 8)) * (BM * 16) + (uint32_t)r * 16u;
+      auto put = [&](const uint32_t (&pk)[16], int c) {
+        if (to_smem) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + (uint32_t)(c * 4 + i) * (BM * 16)),
+                         "r"(pk[4 * i]), "r"(pk[4 * i + 1]), "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3]) : "memory");
+        } else {
+          tmem_st16(dst + c * 16, pk);
+        }
+      };
       for (int c = 0; c < nchunk; c += 2) {
         if (c + 1 < nchunk) load_chunk(vb, p + (int64_t)(c + 1) * 32 * L.S, L.S, valid);
         {
           uint32_t pk[16];
           pack_chunk(va, pk, ss, dd, !(ablate & 4));
-          if (!(ablate & 8)) tmem_st16(dst + c * 16, pk);
+          if (!(ablate & 8)) put(pk, c);
         }
         if (c + 1 < nchunk) {
           if (c + 2 < nchunk) load_chunk(va, p + (int64_t)(c + 2) * 32 * L.S, L.S, valid);
           uint32_t pk[16];
           pack_chunk(vb, pk, ss, dd, !(ablate & 4));
-          if (!(ablate & (8 | 128))) tmem_st16(dst + (c + 1) * 16, pk);
+          if (!(ablate & (8 | 128))) put(pk, c + 1);
         }
       }
-      tmem_st_wait();
+      if (to_smem) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> the MMA's reads
+      else tmem_st_wait();
       if constexpr (DBG) { if (out.trace && tl < TRACE_SWEEPS && warp == Cfg::LD_WARP0 && lane == 0) out.trace[((size_t)blockIdx.x * TRACE_SWEEPS + tl) * 8 + 5] = clock64(); }
       mbar_wait_sleep(norm_empty(ab), a_phase ^ 1);   // the epilogue has read the previous norms of this buffer
       norm_s[((ab * 2 + h) * 2 + 0) * BM + r] = ss;
@@ -593,7 +627,9 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(norm_full(ab));
-        if (CG == 1) mbar_arrive(a_full(ab)); else mbar_arrive_cluster(af_bar + 8u * ab);
+        if (CG == 1) mbar_arrive(a_full(ab));
+        else if (to_smem) mbar_arrive_cluster_release(af_bar + 8u * ab);   // (shared-memory A: read by an MMA the leader CTA issues)
+        else mbar_arrive_cluster(af_bar + 8u * ab);
       }
     }
     pdl_wait();
@@ -603,7 +639,7 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
     // of every tile and keeps its own running maximum / candidate list; the two lists meet in finalize_row.
     const int q = warp & 3, g = (warp - Cfg::EP_WARP0) >> 2;
     const int row_in_tile = q * 32 + lane;
-    constexpr uint32_t CAP = (uint32_t)park_cap(BN);
+    constexpr uint32_t CAP = (uint32_t)park_cap(BN, ASM);
     constexpr uint32_t LIST_BYTES = CAP * ENTRY_BYTES;            // one group's store
     const uint32_t pk_base = smem_base + lay.list + (uint32_t)g * LIST_BYTES + (uint32_t)row_in_tile * 16u;   // entry 0, float4 0
     const uint32_t pk_hdr = smem_base + lay.list + (uint32_t)g * LIST_BYTES + HDR_OFFSET + (uint32_t)row_in_tile * 8u;
@@ -677,20 +713,23 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
         // One 32-column chunk of this thread's row.  Fast path: maxima of the 8 groups of 4 columns (16 ops) and
         // their maximum (4 ops).  A chunk can only contribute candidates if its maximum reaches (running max - margin);
         // then it is parked whole (see ENTRY_BYTES).
-        auto process = [&](uint32_t (&ra)[32], const int cbase) {
-          float v[32];
+        // maximum of one 32-column chunk: maxima of the 8 groups of 4 (FMNMX3 pairs) and their maximum
+        auto chunk_max = [&](const uint32_t (&r)[32]) {
+          float gm[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
+          for (int i = 0; i < 8; ++i)
+            gm[i] = fmaxf(fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), __uint_as_float(r[4 * i + 2])),
+                          __uint_as_float(r[4 * i + 3]));
+          return fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(fmaxf(gm[3], gm[4]), gm[5]), fmaxf(gm[6], gm[7])));
+        };
+        // candidate path of one chunk with maximum m
+        auto park_chunk = [&](const uint32_t (&r)[32], const float m, const int cbase) {
           if constexpr (DBG) {
             if (out.dbg_scores && row < L.N) {   // diagnostic dump of the raw score tile
 #pragma unroll
-              for (int i = 0; i < 32; ++i) out.dbg_scores[row * K_pad + col0 + cbase + i] = v[i];
+              for (int i = 0; i < 32; ++i) out.dbg_scores[row * K_pad + col0 + cbase + i] = __uint_as_float(r[i]);
             }
           }
-          float gm[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) gm[i] = fmaxf(fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), v[4 * i + 2]), v[4 * i + 3]);
-          const float m = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), fmaxf(fmaxf(fmaxf(gm[3], gm[4]), gm[5]), fmaxf(gm[6], gm[7])));
           if (m >= fmaxf(runmax, peer_max) - margin && !(ablate & 2)) {
             if (m > runmax + margin) { cnt = 0; dropmax = -FLT_MAX; }   // everything parked so far is stale
             runmax = fmaxf(runmax, m);
@@ -711,21 +750,31 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
               const uint32_t eoff = slot * ENTRY_BYTES;
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pk_base + eoff + (uint32_t)i * (BM * 16)),
-                             "f"(v[4 * i]), "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pk_base + eoff + (uint32_t)i * (BM * 16)),
+                             "r"(r[4 * i]), "r"(r[4 * i + 1]), "r"(r[4 * i + 2]), "r"(r[4 * i + 3]) : "memory");
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(pk_hdr + eoff), "r"((uint32_t)(col0 + cbase)), "r"(__float_as_uint(m)) : "memory");
 #pragma unroll
               for (uint32_t e = 0; e < CAP; ++e) pmax[e] = (slot == e) ? m : pmax[e];
             }
           }
         };
+        // One 32-column chunk of this thread's row.  Fast path: its maximum (20 ops).  A chunk can only contribute
+        // candidates if its maximum reaches (running max - margin); then it is parked whole (see ENTRY_BYTES).
+        auto process = [&](const uint32_t (&r)[32], const int cbase) { park_chunk(r, chunk_max(r), cbase); };
 
+        // (Measured and dropped with three accumulators: rolling the two chunks through the register sets — the tcgen05.ld
+        //  of one in flight while the other is processed, the next tile's first chunk requested before this tile's second
+        //  is looked at.  It takes the tensor-memory load latency off the epilogue's path but hands the accumulator back
+        //  half a tile later: c2 123.0 -> 129.2 us on the same box.)
         if constexpr (WIDE) {
           // both 32-column chunks of this group's half tile at once; the accumulator goes back to the MMA warp as
           // soon as they are in registers (the other group does the same with its half), the max trees run after
           load_half_tile(tl, j);
-          process(ra, 0);
-          process(rb, 32);
+          // (both maxima first: 36 independent max operations in flight instead of two dependent trees separated by
+          //  the divergent candidate path)
+          const float m_a = chunk_max(ra), m_b = chunk_max(rb);
+          park_chunk(ra, m_a, 0);
+          park_chunk(rb, m_b, 32);
           asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(live_own), "r"(__float_as_uint(runmax)), "r"(tl) : "memory");   // (racy by design: any earlier value of THIS sweep is a valid lower bound)
         } else {
           // BN/32 chunks of 32 columns; the tcgen05.ld of the next chunk overlaps the max tree of this
@@ -831,20 +880,20 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------
-template <int CG, int BN>
+template <int CG, int BN, bool ASM = false>
 static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const float* e_max,
                          float tau, int K, int K_pad, int D, int n_cand, int nacc, int abuf,
                          const ScreenOut& out, cudaStream_t st) {
   static_assert(BN == 128 || BN == 96 || BN == 64, "epilogue is written for 2 or 3 chunks of 32 columns per group (narrower / odd widths were measured and dropped: profiles/r01_screen_history.md)");
   const int dblk = D / 64;
-  const ScreenSmem lay = screen_smem_layout(dblk, CG, BN);
+  const ScreenSmem lay = screen_smem_layout(dblk, CG, BN, ASM);
   CCVSQ_REQUIRE(lay.nslots >= 1, CCVSQ_UNSUPPORTED, "screen: D=%d leaves room for %d B slots", D, lay.nslots);
   EncodeTiledFn enc;
   if (int rc = get_encode_fn(&enc)) return rc;
   CUtensorMap mb, mx;
   if (int rc = make_map(enc, &mb, E_bf16, K_pad, D + SCREEN_EXT, 64, BN / CG, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   if (int rc = make_map(enc, &mx, E_bf16, K_pad, D + SCREEN_EXT, 8, BN / CG, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-  auto kern = (out.dbg_cand || out.trace) ? screen_kernel<CG, true, BN> : screen_kernel<CG, false, BN>;
+  auto kern = (out.dbg_cand || out.trace) ? screen_kernel<CG, true, BN, ASM> : screen_kernel<CG, false, BN, ASM>;
   if (int rc = enable_smem(kern, lay.total)) return rc;
   const int64_t rows_per_group = (int64_t)BM * CG;
   const int64_t group_tiles = (L.N + rows_per_group - 1) / rows_per_group;
@@ -880,9 +929,14 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
 // times, so three accumulators come first.  Wide tiles (BN = 128): two accumulators + abuf A buffers, nothing else.
 // Short code sweeps take the wide plan (see the note at `BM`); long sweeps (K >= 2304) keep 96-column tiles with three
 // accumulators and one A buffer (fewest hand-offs per code; MMA-bound at 86-90 % of the BF16 burst peak).
+// Wide tiles with THREE accumulators (nacc = 3, abuf = 2): one A buffer in tensor memory, the other in shared memory; row
+// tiles alternate between them (TS-form / SS-form MMAs) — the third accumulator lets the MMA warp run through the
+// epilogue's end-of-sweep work.
 struct ScreenPlan { int bn, nacc, abuf; };
 static bool plan_fits(int D, int bn, int nacc, int abuf) {
   const int a_cols = D / 2;
+  if (bn == 128 && nacc == 3)
+    return abuf == 2 && D <= 256 && 3 * 128 + a_cols <= (int)TMEM_COLS && screen_smem_layout(D / 64, 2, 128, true).nslots >= 2;
   if (bn == 128) return nacc == 2 && D <= 256 && 2 * 128 + abuf * a_cols <= (int)TMEM_COLS;   // (D = 512: one B slot left)
   return nacc * bn + 8 + abuf * a_cols <= (int)TMEM_COLS;
 }
@@ -902,9 +956,9 @@ static ScreenPlan plan_screen(int K, int D) {
   const bool long_sweep = (K + 95) / 96 >= 24;
   ScreenPlan best = {96, 2, 1};
   const ScreenPlan order_long[] = {{96, 3, 2}, {96, 3, 1}, {64, 3, 2}, {64, 3, 1}, {96, 2, 2}, {96, 2, 1}};
-  const ScreenPlan order_short[] = {{128, 2, 2}, {128, 2, 1}, {96, 3, 2}, {64, 3, 2}, {96, 3, 1}, {64, 3, 1}, {96, 2, 2}, {96, 2, 1}};
+  const ScreenPlan order_short[] = {{128, 3, 2}, {128, 2, 2}, {128, 2, 1}, {96, 3, 2}, {64, 3, 2}, {96, 3, 1}, {64, 3, 1}, {96, 2, 2}, {96, 2, 1}};
   const ScreenPlan* order = long_sweep ? order_long : order_short;
-  const int n_order = long_sweep ? 6 : 8;
+  const int n_order = long_sweep ? 6 : 9;
   for (int i = 0; i < n_order; ++i) {
     const ScreenPlan& p = order[i];
     if (forced_bn && p.bn != forced_bn) continue;
@@ -942,10 +996,12 @@ static int screen_impl(const float* z, ccvsq_layout lay, const void* E_bf16, con
                 "screen: D=%d does not fit the tensor-memory budget", D);
   cudaStream_t st = (cudaStream_t)stream;
   if (cta_group == 2) {
+    if (pl.bn == 128 && pl.nacc == 3) return launch_screen<2, 128, true>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
     if (pl.bn == 128) return launch_screen<2, 128>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
     if (pl.bn == 64) return launch_screen<2, 64>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
     return launch_screen<2, 96>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
   }
+  if (pl.bn == 128 && pl.nacc == 3) return launch_screen<1, 128, true>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
   if (pl.bn == 128) return launch_screen<1, 128>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
   if (pl.bn == 64) return launch_screen<1, 64>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
   return launch_screen<1, 96>(E_bf16, z, L, e_max, margin_scale, K, K_pad, D, n_cand, pl.nacc, pl.abuf, out, st);
