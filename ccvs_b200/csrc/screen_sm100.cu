@@ -210,6 +210,37 @@ __device__ __forceinline__ void scan_unique(uint32_t base, uint32_t hdr, uint32_
   }
 }
 
+// The same scan for the wide plan, with the liveness test on the REGISTER copy of the chunk maxima (the header is only
+// read for a live chunk: the row's first code of that chunk) and the loop over the entries fully unrolled.
+template <int CAPN>
+__device__ __forceinline__ void scan_unique_reg(uint32_t base, uint32_t hdr, uint32_t n, const float (&pmax)[CAPN], float thr,
+                                                uint32_t& within, uint32_t& code_sum) {
+#pragma unroll
+  for (uint32_t e = 0; e < (uint32_t)CAPN; ++e) {
+    if (e < n && pmax[e] >= thr) {
+      const uint32_t eb = base + e * ENTRY_BYTES;
+      float sc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[i][0]), "=f"(sc[i][1]), "=f"(sc[i][2]), "=f"(sc[i][3])
+                     : "r"(eb + (uint32_t)i * (BM * 16)));
+      uint32_t code;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(code) : "r"(hdr + e * ENTRY_BYTES));
+      uint32_t w = 0, pos = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool p = sc[i][u] >= thr;
+          w += p ? 1u : 0u;
+          pos += p ? (uint32_t)(4 * i + u) : 0u;
+        }
+      within += w;
+      code_sum += w * code + pos;          // (meaningful only when the total count is exactly one)
+    }
+  }
+}
+
 // General end-of-sweep path of one row (rows with more than one code inside the margin, dropped chunks, diagnostics):
 // every parked code with score >= runmax - margin, sorted by (score desc, code asc), at most n_cand of them, goes to the
 // re-scoring queue.  Kept out of line (and rolled) so the per-tile loop stays small in the instruction cache.
@@ -821,34 +852,44 @@ screen_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__
           // tile old: a LOWER threshold, i.e. a superset — and exact for the group that holds the row's maximum, whose
           // result is the one that decides below)
           const float thr_s = fmaxf(runmax, peer_running_max(tl)) - margin;
-          if (!(ablate & 32)) scan_unique(pk_base, pk_hdr, cnt, thr_s, within, code1); else within = 1;
+          if (!(ablate & 32)) scan_unique_reg<(int)CAP>(pk_base, pk_hdr, cnt, pmax, thr_s, within, code1); else within = 1;
           if (dropmax >= thr_s) within |= 0x80000000u;             // a dropped chunk may hold a code inside the margin
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_own), "r"(__float_as_uint(runmax)), "r"(code1), "r"(within), "r"(cnt) : "memory");
         if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 3);
         if (!(ablate & 64)) named_bar_sync(1 + q, 64);
         if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 4);
-        if ((lane >> 4) == g && row < L.N) {
+        bool slow_row;
+        {
+          // every lane evaluates its row (both warps of the pair hold the same 32 rows and see the same two states, so
+          // they agree on which rows need the general path); the rows are then split between the two warps
           uint32_t rm_pb, code_p, w_p, n_p;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rm_pb), "=r"(code_p), "=r"(w_p), "=r"(n_p) : "r"(st_par));
           const float rm_p = __uint_as_float(rm_pb);
           const bool own_max = runmax >= rm_p;
           const float rmax = fmaxf(runmax, rm_p), thr = rmax - margin;
           const uint32_t w_top = own_max ? within : w_p;            // count (and drop bit) of the group holding the maximum
-          if (w_top == 1u && fminf(runmax, rm_p) < thr && !out.dbg_cand) {
-            if (out.idx) out.idx[row] = (int64_t)(own_max ? code1 : code_p);
-          } else {
-            RowLists rl;
-            const uint32_t b0 = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
-            const uint32_t h0 = smem_base + lay.list + HDR_OFFSET + (uint32_t)row_in_tile * 8u;
-            rl.base[0] = b0; rl.base[1] = b0 + LIST_BYTES;
-            rl.hdr[0] = h0;  rl.hdr[1] = h0 + LIST_BYTES;
-            rl.n[g] = cnt;   rl.n[1 - g] = n_p;
-            finalize_row<2>(rl, rmax, margin, ((within | w_p) & 0x80000000u) != 0, n_cand, row, out);
+          const bool fast = w_top == 1u && fminf(runmax, rm_p) < thr && !out.dbg_cand;
+          slow_row = !fast && row < L.N;
+          if ((lane >> 4) == g && row < L.N) {
+            if (fast) {
+              if (out.idx) out.idx[row] = (int64_t)(own_max ? code1 : code_p);
+            } else {
+              RowLists rl;
+              const uint32_t b0 = smem_base + lay.list + (uint32_t)row_in_tile * 16u;
+              const uint32_t h0 = smem_base + lay.list + HDR_OFFSET + (uint32_t)row_in_tile * 8u;
+              rl.base[0] = b0; rl.base[1] = b0 + LIST_BYTES;
+              rl.hdr[0] = h0;  rl.hdr[1] = h0 + LIST_BYTES;
+              rl.n[g] = cnt;   rl.n[1 - g] = n_p;
+              finalize_row<2>(rl, rmax, margin, ((within | w_p) & 0x80000000u) != 0, n_cand, row, out);
+            }
           }
         }
         if (q == 0) CCVSQ_TILE_STAMP(tl, 8 + 2 * g, 5);
-        if (!(ablate & 64)) named_bar_sync(1 + q, 64);              // the partner has read this group's store: it may be reused
+        // the partner has read this group's store and state: they may be reused.  (Measured: taking this barrier only when
+        // some row of the pair went the general way — both warps can compute that vote — changes nothing, 121.1 vs 121.3 us.)
+        (void)slow_row;
+        if (!(ablate & 64)) named_bar_sync(1 + q, 64);
         if (q == 0) CCVSQ_TILE_STAMP(tl, 9 + 2 * g, 3);
       } else {
         if (row < L.N) {

@@ -18,6 +18,7 @@
 //   instead of the 7 passes + 4-byte accesses of the generic tile kernels.
 // Row-major latents (S == 1): rows are contiguous; a flat loop over 16-byte chunks, no shared memory.
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ccvsq {
@@ -459,6 +460,27 @@ __global__ void __launch_bounds__(FNT, MODE == MODE_BACKWARD ? 3 : 4) rowsw_kern
     k[i] = kk;
     if (a.counts && valid[i] && lane == 0 && (IS_ASSIGN(MODE) || MODE == MODE_STATS)) atomicAdd(a.counts + kk, 1);
   }
+  if constexpr (MODE == MODE_GATHER && RPW <= 2) {
+    // decode of short inputs (the launcher picks RPW <= 2 there): every chunk of the warp's rows in flight before the
+    // first store — with one row per warp and a chunk at a time a lane has ONE 16-byte load outstanding and the kernel is
+    // bound by the L2 round trip (the D = 512 Kinetics shard: 0.62 of the copy bandwidth where a device fill reaches 0.89)
+    if (QL <= 4 && !a.pos) {
+      float4 ev[4][RPW];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < RPW; ++i)
+          if (c < QL && valid[i]) ev[c][i] = __ldg(reinterpret_cast<const float4*>(a.E) + (size_t)k[i] * Q + lane + 32 * c);
+      if (a.out) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < RPW; ++i)
+            if (c < QL && valid[i]) __stcs(reinterpret_cast<float4*>(a.out) + (n_base + i) * Q + lane + 32 * c, ev[c][i]);
+      }
+      return;
+    }
+  }
   float coef = 0.f;
   if (MODE == MODE_BACKWARD) coef = __ldg(a.g_loss) * a.coef_scale;
   float acc = 0.f;
@@ -563,6 +585,8 @@ static int launch_rows4(const StreamArgs& a, const Lay& L, cudaStream_t st) {
     const int64_t slots = (int64_t)kNumSMs * 8;
     int rpw = 4;
     while (rpw > 1 && (L.N + rpw * (FNT / 32) - 1) / (rpw * (FNT / 32)) < 4 * slots) rpw >>= 1;
+    static const int forced_rpw = [] { const char* e = getenv("CCVSQ_ROWS_RPW"); return e ? atoi(e) : 0; }();   // (A/B runs)
+    if (forced_rpw == 1 || forced_rpw == 2 || forced_rpw == 4) rpw = forced_rpw;
     const int64_t blocks = (L.N + rpw * (FNT / 32) - 1) / (rpw * (FNT / 32));
     CCVSQ_REQUIRE(blocks < (1ll << 31), CCVSQ_BAD_SHAPE, "stream kernel: %lld CTAs exceed the grid limit", (long long)blocks);
     if (rpw == 4) CCVSQ_CUDA(launch_pdl(rowsw_kernel<MODE, 4>, dim3((unsigned)blocks), dim3(FNT), 0, st, a, L.N, L.D));
