@@ -80,6 +80,8 @@ SIGNATURES = {
     "ccvsq_rescore": (c_int, [_P, Layout, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "ccvsq_search_exact_rows": (c_int, [_P, Layout, _P, _P, c_int, _P, _P, c_int64, _P, _P]),
     "ccvsq_assign": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, _P, _P]),
+    "ccvsq_assign_normalized": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, _P, _P]),
+    "ccvsq_backward_normalized": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "ccvsq_gather": (c_int, [_P, _P, c_int, Layout, _P, _P, _P]),
     "ccvsq_backward_dz": (c_int, [_P, Layout, _P, c_int, _P, _P, _P, _P, _P]),
     "ccvsq_code_stats": (c_int, [_P, Layout, _P, c_int, _P, c_float, _P, _P, _P]),

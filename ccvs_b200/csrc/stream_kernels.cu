@@ -275,6 +275,111 @@ __global__ void __launch_bounds__(NT) backward_dz_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// normalize=True (quantize.py:56-57) with any `mult`: the quantized vector of a position is the CONCATENATION of its
+// `mult` code rows divided by its L2 norm over all C channels,  u = y / ||y||,  y = [E[k_0] | ... | E[k_{mult-1}]].
+// A position tile holds all sub-rows of its positions, so the norm, the straight-through value, the squared error
+// and — in the backward — the chain rule through the normalisation are per-warp work on one position:
+//   forward   z_q = fl(z + fl(u - z)),  sq_err += sum (u - z)^2,  counts[k]++
+//   backward  dz  = g_zq + (2 g/M)(z - u)
+//             dL/dy = (2 beta g/M)(1/||y||)(u (u.z) - z)   ->   resid[k,:] += (z - (u.z) u) / ||y||   (dE = -(2 beta g/M) resid)
+// One warp per position: pass 1 over the code rows for ||y||^2 (and u.z in the backward), pass 2 for the outputs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) assign_norm_kernel(const float* __restrict__ z, Lay L, const float* __restrict__ E, int K,
+                                                         const int64_t* __restrict__ idx, float* __restrict__ zq,
+                                                         double* __restrict__ sq_err, int32_t* __restrict__ counts) {
+  extern __shared__ float tile[];
+  __shared__ float red[NW];
+  const int CP = L.C + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int np = (int)min((int64_t)PT, L.P - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tile_load(z, L, p0, np, tile);
+  __syncthreads();
+  float acc = 0.f;
+  for (int p = warp; p < np; p += NW) {
+    const int64_t n0 = (p0 + p) * L.mult;
+    float ss = 0.f;
+    for (int m = 0; m < L.mult; ++m) {
+      int64_t k = idx[n0 + m];
+      k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+      const float* e = E + (size_t)k * L.D;
+      for (int j = lane; j < L.D; j += 32) { const float v = __ldg(e + j); ss = fmaf(v, v, ss); }
+      if (counts && lane == 0) atomicAdd(counts + k, 1);
+    }
+    const float nrm = sqrtf(warp_sum(ss));
+    for (int m = 0; m < L.mult; ++m) {
+      int64_t k = idx[n0 + m];
+      k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+      const float* e = E + (size_t)k * L.D;
+      float* t = tile + p * CP + m * L.D;
+      for (int j = lane; j < L.D; j += 32) {
+        const float zv = t[j];
+        const float diff = __fsub_rn(__fdiv_rn(__ldg(e + j), nrm), zv);   // fl(y/||y|| - z)
+        t[j] = __fadd_rn(zv, diff);                                       // quantize.py:64 on the normalised vector
+        acc = fmaf(diff, diff, acc);
+      }
+    }
+  }
+  if (sq_err) {
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+  }
+  __syncthreads();
+  if (sq_err && threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w];
+    atomicAdd(sq_err, (double)s);
+  }
+  if (zq) tile_store(zq, nullptr, L, p0, np, tile);
+}
+
+__global__ void __launch_bounds__(NT) backward_norm_kernel(const float* __restrict__ z, Lay L, const float* __restrict__ E, int K,
+                                                           const int64_t* __restrict__ idx, const float* __restrict__ g_zq,
+                                                           const float* __restrict__ g_loss, float inv_M2,
+                                                           float* __restrict__ dz, float* __restrict__ resid) {
+  extern __shared__ float tile[];
+  const int CP = L.C + 1;
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int np = (int)min((int64_t)PT, L.P - p0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float coef = __ldg(g_loss) * inv_M2;
+  tile_load(z, L, p0, np, tile);
+  __syncthreads();
+  for (int p = warp; p < np; p += NW) {
+    const int64_t n0 = (p0 + p) * L.mult;
+    float ss = 0.f, yz = 0.f;
+    for (int m = 0; m < L.mult; ++m) {
+      int64_t k = idx[n0 + m];
+      k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+      const float* e = E + (size_t)k * L.D;
+      const float* t = tile + p * CP + m * L.D;
+      for (int j = lane; j < L.D; j += 32) {
+        const float v = __ldg(e + j);
+        ss = fmaf(v, v, ss);
+        yz = fmaf(v, t[j], yz);
+      }
+    }
+    const float nrm = sqrtf(warp_sum(ss));
+    const float q = warp_sum(yz) / nrm;                 // u . z
+    for (int m = 0; m < L.mult; ++m) {
+      int64_t k = idx[n0 + m];
+      const bool in_range = k >= 0 && k < K;
+      k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+      const float* e = E + (size_t)k * L.D;
+      float* t = tile + p * CP + m * L.D;
+      for (int j = lane; j < L.D; j += 32) {
+        const float zv = t[j], u = __ldg(e + j) / nrm;
+        if (resid && in_range) atomicAdd(resid + (size_t)k * L.D + j, (zv - q * u) / nrm);
+        t[j] = coef * (zv - u);
+      }
+    }
+  }
+  __syncthreads();
+  if (dz) tile_store(dz, g_zq, L, p0, np, tile);
+}
+
+// ------------------------------------------------------------------------------------------------
 // code_stats: resid[k,:] += x_n - sub*E[k]; counts[k]++      (global fp32 reductions)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) code_stats_kernel(const float* __restrict__ x, Lay L,
@@ -654,6 +759,36 @@ extern "C" int ccvsq_assign(const float* z, ccvsq_layout lay, const float* E, in
   StreamArgs a = {};
   a.x = z; a.E = E; a.idx = idx; a.out = zq_out; a.sq_err = sq_err; a.counts = counts; a.K = K;
   return stream_launch(MODE_ASSIGN, a, L, (cudaStream_t)stream);
+}
+
+extern "C" int ccvsq_assign_normalized(const float* z, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
+                                       float* zq_out, double* sq_err, int32_t* counts, void* stream) {
+  CCVSQ_REQUIRE(z && E && idx, CCVSQ_NULL_POINTER, "assign_normalized: null pointer");
+  CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "assign_normalized: K=%d", K);
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  const size_t smem = tile_smem_bytes(L);
+  if (int rc = enable_smem(assign_norm_kernel, smem)) return rc;
+  assign_norm_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, (cudaStream_t)stream>>>(z, L, E, K, idx, zq_out, sq_err, counts);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
+}
+
+extern "C" int ccvsq_backward_normalized(const float* z, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
+                                         const float* g_zq, const float* g_loss, float* dz, float* resid, void* stream) {
+  CCVSQ_REQUIRE(z && E && idx && g_loss, CCVSQ_NULL_POINTER, "backward_normalized: null pointer");
+  CCVSQ_REQUIRE(K > 0, CCVSQ_BAD_SHAPE, "backward_normalized: K=%d", K);
+  if (!dz && !resid) return CCVSQ_OK;
+  Lay L;
+  if (int rc = make_lay(lay, &L)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (resid) CCVSQ_CUDA(cudaMemsetAsync(resid, 0, (size_t)K * L.D * sizeof(float), st));
+  const size_t smem = tile_smem_bytes(L);
+  if (int rc = enable_smem(backward_norm_kernel, smem)) return rc;
+  backward_norm_kernel<<<(unsigned)cdiv(L.P, PT), NT, smem, st>>>(z, L, E, K, idx, g_zq, g_loss,
+                                                                  (float)(2.0 / ((double)L.P * L.C)), dz, resid);
+  CCVSQ_LAUNCH_CHECK();
+  return CCVSQ_OK;
 }
 
 extern "C" int ccvsq_backward_dz(const float* z, ccvsq_layout lay, const float* E, int K,

@@ -33,6 +33,7 @@ _KERNELS_PER_CALL = {
     "ccvsq_prepare_codebook": 1, "ccvsq_search_exact": 1, "ccvsq_screen": 1, "ccvsq_screen_trace": 1, "ccvsq_screen_debug": 1, "ccvsq_rescore": 1,
     "ccvsq_search_exact_rows": 1, "ccvsq_assign": 1, "ccvsq_gather": 1, "ccvsq_backward_dz": 1, "ccvsq_code_stats": 1,
     "ccvsq_finalize": 1, "ccvsq_ema_update": 2, "ccvsq_ema_update_packed": 2, "ccvsq_code_stats_fixed": 3,
+    "ccvsq_assign_normalized": 1, "ccvsq_backward_normalized": 1,
     "ccvsq_gather_add": 1, "ccvsq_polyak": 1, "ccvsq_peer_publish": 1, "ccvsq_peer_ema_update": 2,
     "ccvsq_encoder_tail_prepare": 1, "ccvsq_encoder_tail": 1,
     "ccvsq_quantize_forward": 0, "ccvsq_quantize_backward": 0,   # composites: counted by their wrappers
@@ -337,6 +338,36 @@ def assign(z: torch.Tensor, lay: Layout, weight: torch.Tensor, idx: torch.Tensor
     counts = torch.zeros(K, dtype=torch.int32, device=dev) if want_counts else None
     _call("ccvsq_assign", _ptr(z), lay, _ptr(weight), K, _ptr(idx), _ptr(zq), _ptr(sq), _ptr(counts), _stream(dev))
     return zq, sq, counts
+
+
+def assign_normalized(z: torch.Tensor, lay: Layout, weight: torch.Tensor, idx: torch.Tensor):
+    """`assign` for normalize=True (quantize.py:56-57, any mult): the quantized vector of a position is the concatenation of
+    its code rows divided by its L2 norm over all channels.  Returns z_q, sum of squared errors (fp64 [1]), counts."""
+    _req(z, torch.float32, "z")
+    _req(idx, torch.int64, "idx")
+    dev = z.device
+    K = weight.shape[0]
+    zq = torch.empty_like(z)
+    sq = torch.zeros(1, dtype=torch.float64, device=dev)
+    counts = torch.zeros(K, dtype=torch.int32, device=dev)
+    _call("ccvsq_assign_normalized", _ptr(z), lay, _ptr(weight), K, _ptr(idx), _ptr(zq), _ptr(sq), _ptr(counts), _stream(dev))
+    return zq, sq, counts
+
+
+def backward_normalized(z: torch.Tensor, lay: Layout, weight: torch.Tensor, idx: torch.Tensor, g_zq: Optional[torch.Tensor],
+                        g_loss: torch.Tensor, beta: float, want_dz: bool = True, want_dE: bool = True):
+    """Backward of the normalize=True forward: dz = g_zq + (2 g/M)(z - u) and dE through the normalisation
+    (ccvsq_backward_normalized + ccvsq_finalize)."""
+    dev = z.device
+    K, D = weight.shape
+    dz = torch.empty_like(z) if want_dz else None
+    resid = torch.empty(K, D, dtype=torch.float32, device=dev) if want_dE else None
+    _call("ccvsq_backward_normalized", _ptr(z), lay, _ptr(weight), K, _ptr(idx), _ptr(g_zq), _ptr(g_loss), _ptr(dz), _ptr(resid),
+          _stream(dev))
+    dE = None
+    if want_dE:
+        dE, _, _ = finalize(K, D, float(z.numel()), float(lay.rows), beta, resid=resid, g_loss=g_loss, want_dE=True)
+    return dz, dE
 
 
 def gather(code: torch.Tensor, weight: torch.Tensor, out_lay: Optional[Layout] = None,

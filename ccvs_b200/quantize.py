@@ -192,24 +192,45 @@ class _AssignFn(torch.autograd.Function):
         return dz, dT, None, None
 
 
-class _GatherFn(torch.autograd.Function):
-    """E[idx] written in z's layout, with the embedding backward as a per-code scatter-add.
-    Used by the `normalize=True` variant, whose remaining elementwise graph (quantize.py:56-64)
-    stays in autograd."""
+class _NormAssignFn(torch.autograd.Function):
+    """normalize=True with mult > 1 (quantize.py:56-64): a position's quantized vector is the concatenation of its `mult`
+    code rows divided by its L2 norm over ALL channels, so it is not a function of one code and no table can be
+    pre-normalised.  Forward (z_q, loss, perplexity, counts) and backward (dz, dE through the normalisation) run in the
+    position-tile kernels `ccvsq_assign_normalized` / `ccvsq_backward_normalized`; no N-sized torch op remains."""
 
     @staticmethod
-    def forward(ctx, weight, idx, lay):
-        out, _ = ops.gather(idx, weight, lay if lay.S > 1 else None)
+    def forward(ctx, z, weight, idx, beta, mult):
+        K, D = weight.shape
+        if z.ndim >= 4:
+            lay = ops.layout_of(z.shape, D, mult)
+        else:
+            # the reference normalises over the LAST dim of the tensor as it is (quantize.py:57 after `.view(z.shape)`):
+            # a "position" is one row of that dim, holding last / D consecutive codes
+            last = int(z.shape[-1])
+            if last % D != 0:
+                raise ValueError(f"normalize=True needs the last dim ({last}) to hold whole codes of {D} channels")
+            lay = Layout(z.numel() // last, last, 1, last // D)
+        zq, sq, counts = ops.assign_normalized(z, lay, weight.detach(), idx)
+        _, loss, perp = ops.finalize(K, D, float(z.numel()), float(lay.rows), beta, counts=counts, sq_err=sq,
+                                     want_loss=True, want_perplexity=True)
         ctx.lay = lay
-        ctx.K = weight.shape[0]
-        ctx.save_for_backward(idx)
-        return out
+        ctx.beta = beta
+        ctx.save_for_backward(z, weight, idx)
+        ctx.mark_non_differentiable(perp, counts)
+        return zq, loss, perp, counts
 
     @staticmethod
-    def backward(ctx, g):
-        (idx,) = ctx.saved_tensors
-        resid, _ = ops.code_stats(g.contiguous(), ctx.lay, None, ctx.K, idx, sub=0.0, want_counts=False)
-        return resid, None, None
+    def backward(ctx, g_zq, g_loss, _gp, _gc):
+        z, weight, idx = ctx.saved_tensors
+        if g_loss is None:
+            g_loss = torch.zeros((), dtype=torch.float32, device=z.device)
+        g_loss = g_loss.to(torch.float32).contiguous()
+        want_dz, want_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (want_dz or want_dE):
+            return None, None, None, None, None
+        g = None if (g_zq is None or not want_dz) else g_zq.to(torch.float32).contiguous()
+        dz, dE = ops.backward_normalized(z, ctx.lay, weight.detach(), idx, g, g_loss, ctx.beta, want_dz, want_dE)
+        return dz, dE, None, None, None
 
 
 class VectorQuantizer(nn.Module):
@@ -339,18 +360,10 @@ class VectorQuantizer(nn.Module):
             zq, loss, perp, counts = _AssignFn.apply(z, table, idx, self.beta)
             self.last_counts = counts
             return zq, loss, idx, perp
-        # mult > 1: the norm runs over the concatenation of several codes; gather in our kernel, the normalisation
-        # and its chain rule stay in autograd
-        with torch.no_grad():
-            counts = torch.bincount(idx, minlength=self.n_e).to(torch.int32)
-            _, _, perp = ops.finalize(self.n_e, self.e_dim, float(z.numel()), float(lay.rows), self.beta, counts=counts,
-                                      want_perplexity=True)
+        # mult > 1: the norm runs over the concatenation of several codes — assign / backward kernels that normalise per
+        # position (every sub-row of a position sits in one position tile)
+        zq, loss, perp, counts = _NormAssignFn.apply(z, w, idx, self.beta, self.mult)
         self.last_counts = counts
-        zq = _GatherFn.apply(w, idx, lay).view(z.shape)
-        ch_dim = -3 if z.ndim >= 4 else -1
-        zq = zq / torch.norm(zq, p=2, dim=ch_dim, keepdim=True)                     # quantize.py:56-57
-        loss = torch.mean((zq.detach() - z) ** 2) + self.beta * torch.mean((zq - z.detach()) ** 2)
-        zq = z + (zq - z).detach()
         return zq, loss, idx, perp
 
     @torch.no_grad()

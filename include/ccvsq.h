@@ -215,6 +215,17 @@ int ccvsq_code_stats_fixed(const float* x, ccvsq_layout lay, const float* E, int
                            float sub, int64_t* acc, float* amax_scratch, float* resid, int32_t* counts,
                            void* stream);
 
+/* ---- normalize=True (quantize.py:56-57), any mult: assign / backward on the L2-normalised concatenation ----------
+ * The quantized vector of a position is u = y/||y||_2 with y the concatenation of its `mult` code rows (norm over all C
+ * channels, quantize.py:57).  ccvsq_assign_normalized: z_q = fl(z + fl(u - z)), sq_err += sum (u - z)^2, counts — the
+ * same outputs as ccvsq_assign, ready for ccvsq_finalize.  ccvsq_backward_normalized: dz = g_zq + (2 g/M)(z - u) and
+ * resid[k,:] = sum_{idx=k} (z - (u.z) u)/||y||  (ZEROED BY THE CALL), so that ccvsq_finalize's
+ * dE = -(2 beta g/M) resid is the gradient through the normalisation.  dz or resid may be NULL.                   */
+int ccvsq_assign_normalized(const float* z, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
+                            float* zq_out, double* sq_err, int32_t* counts, void* stream);
+int ccvsq_backward_normalized(const float* z, ccvsq_layout lay, const float* E, int K, const int64_t* idx,
+                              const float* g_zq, const float* g_loss, float* dz, float* resid, void* stream);
+
 /* ---- finalize: codebook gradient, loss, perplexity -------------------------------------------
  *   dE[k,:]   = -(2*beta/M) * g_loss * resid[k,:]           (dE may be NULL)
  *   loss      = (1+beta) * sq_err / M                        (quantize.py:60-61; loss may be NULL)

@@ -316,3 +316,43 @@ def test_deterministic_code_sums_are_bit_identical_and_accurate(shape, K, D, mul
     assert torch.equal(counts.cpu().long(), onehot.sum(0).long())
     plain, _ = ops.code_stats_fixed(z.to(DEV), lay, None, K, idx.to(DEV), sub=0.0)
     torch.testing.assert_close(plain.cpu().double(), onehot.t() @ rows.double(), rtol=2e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# normalize=True with mult > 1 (quantize.py:56-57): the norm spans the concatenation of several codes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,K,C,mult", [((4, 64, 8, 8), 256, 64, 2), ((3, 128, 5, 7), 200, 128, 4), ((2, 3, 32, 4, 4), 64, 32, 2),
+                                            ((37, 48), 96, 48, 3)])
+def test_normalized_concatenation_forward_backward_match_oracle(shape, K, C, mult):
+    """Forward (z_q, loss, perplexity) and backward (dz, dE through the normalisation) of `ccvsq_assign_normalized` /
+    `ccvsq_backward_normalized` against the oracle's autograd on the reference op sequence; 4-D, 5-D and 2-D inputs."""
+    D = C // mult
+    g = torch.Generator().manual_seed(17)
+    cb = torch.randn(K, D, generator=g)
+    n_pos = int(np.prod(shape)) // C
+    idx0 = torch.randint(0, K, (n_pos * mult,), generator=g)
+    rows = cb[idx0].view(n_pos, C)
+    rows = rows / rows.norm(dim=1, keepdim=True) + 0.05 * torch.randn(n_pos, C, generator=g)     # near normalised codes
+    if len(shape) >= 4:
+        zl = rows.view(*shape[:-3], shape[-2], shape[-1], C)
+        z = zl.transpose(-3, -1).transpose(-2, -1).contiguous()        # channel-last -> the reference's input layout
+    else:
+        z = rows.view(shape).contiguous()
+    g_zq = torch.randn(shape, generator=g)
+    # oracle
+    zc, cbc = z.clone().requires_grad_(True), cb.clone().requires_grad_(True)
+    ref = vq_oracle.forward(zc, cbc, 0.25, mult=mult, normalize=True)
+    ((ref.z_q * g_zq).sum() + ref.loss * 1.5).backward()
+    # ours
+    vq = VectorQuantizer(K, C, 0.25, mult=mult, normalize=True, search_mode="exact").to(DEV)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(DEV))
+    zd = z.to(DEV).requires_grad_(True)
+    z_q, loss, (perp, _, idx) = vq(zd)
+    ((z_q * g_zq.to(DEV)).sum() + loss * 1.5).backward()
+    assert torch.equal(idx.view(-1).cpu(), ref.indices.view(-1))
+    torch.testing.assert_close(z_q.detach().cpu(), ref.z_q.detach(), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(loss.detach().cpu(), ref.loss.detach(), rtol=1e-5, atol=0)
+    torch.testing.assert_close(perp.cpu(), ref.perplexity.detach(), rtol=1e-5, atol=0)
+    torch.testing.assert_close(zd.grad.cpu(), zc.grad, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(vq.embedding.weight.grad.cpu(), cbc.grad, rtol=1e-4, atol=1e-7)
