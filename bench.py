@@ -814,7 +814,7 @@ def main():
         vqr = _VQ(K, D, 0.25).to(dev).eval()
         with torch.no_grad():
             rows = tail_s(feats0).permute(0, 2, 3, 1).reshape(-1, D)
-            pick = rows[torch.randperm(rows.shape[0], device=dev)[:K]]
+            pick = rows[torch.randint(0, rows.shape[0], (K,), device=dev)]      # (K may exceed the 1 024 positions: with replacement)
             vqr.embedding.weight.copy_(pick + 0.02 * rows.std() * torch.randn_like(pick))
         stepper = ReencodeStep(vqr, tail_s, trunk, code0, (8, 8))
         small["reencode_step"] = {"latents_per_call": 16 * 64, "ms_per_call_eager": time_calls(stepper.eager),

@@ -28,6 +28,8 @@ python tools/time_tail.py > $OUT/time_tail.txt 2>&1
 python tools/tau_cost.py c2 > $OUT/tau_c2.txt 2>&1
 python tools/tau_cost.py c3 > $OUT/tau_c3.txt 2>&1
 python tools/diag_forward.py c2 > $OUT/diag_c2.txt 2>&1
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py tests/test_gpu_hardening.py tests/test_gpu_encoder_tail.py -m gpu -x -q > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?"
+for wl in c3d512 c3 c4; do python tools/time_stream_8x8.py $wl 2>&1 | tail -1; done > $OUT/stream_8x8.txt
+for plan in 128,2,2 128,3,2; do CCVSQ_SCREEN_PLAN=$plan python tools/time_screen.py c2 2>&1 | tail -1; CCVSQ_SCREEN_PLAN=$plan python tools/ab_plan.py c2 2>&1 | tail -1; done > $OUT/plan_ab.txt
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py tests/test_gpu_hardening.py tests/test_gpu_encoder_tail.py tests/test_gpu_train_graph.py -m gpu -x -q > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?"
 tail -3 $OUT/memcheck.log
 python tools/show_bench.py $OUT/bench_c2.json $OUT/bench_c4.json $OUT/bench_c3.json $OUT/bench_c3d512.json $OUT/bench_c1.json $OUT/bench_train.json 2>&1 | tail -40
