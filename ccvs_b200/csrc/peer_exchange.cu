@@ -105,12 +105,19 @@ __global__ void __launch_bounds__(256) peer_ema_counts_kernel(float* __restrict_
   __syncthreads();
   __shared__ float red[8];
   float acc = 0.f;
+  const float* cnt0 = peer_inbox(area, K, D, world, parity, 0) + (size_t)K * D;
+  const size_t stride = peer_stride_floats(K, D);
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    // all W loads in flight, THEN the sum in rank order (a load-add loop is W dependent round trips to L2 / HBM)
+    float v[PEER_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) v[r] = r < world ? __ldcg(cnt0 + r * stride + k) : 0.f;
     float c = 0.f;
-    for (int r = 0; r < world; ++r) c += __ldcg(peer_inbox(area, K, D, world, parity, r) + (size_t)K * D + k);
-    const float v = decay * n_ema[k] + (1.f - decay) * c;
-    n_ema[k] = v;
-    acc += v;
+#pragma unroll
+    for (int r = 0; r < PEER_MAX_WORLD; ++r) c += v[r];          // (+ 0.f for r >= world: exact)
+    const float nv = decay * n_ema[k] + (1.f - decay) * c;
+    n_ema[k] = nv;
+    acc += nv;
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -134,12 +141,23 @@ __global__ void __launch_bounds__(256) peer_ema_embed_kernel(float* __restrict__
   const size_t stride = peer_stride_floats(K, D);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(i * 4 / D);
+    // 8 ranks' loads in flight at a time, then their sums in rank order (fixed order: bit-identical on every rank)
     float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
     float c = 0.f;
-    for (int r = 0; r < world; ++r) {              // fixed order: bit-identical on every rank
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(in0 + r * stride) + i);
-      rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w;
-      c += __ldcg(in0 + r * stride + (size_t)K * D + k);
+    for (int r0 = 0; r0 < world; r0 += 8) {
+      float4 v[8];
+      float cv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const bool on = r0 + r < world;
+        v[r] = on ? __ldcg(reinterpret_cast<const float4*>(in0 + (r0 + r) * stride) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        cv[r] = on ? __ldcg(in0 + (r0 + r) * stride + (size_t)K * D + k) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        rs.x += v[r].x; rs.y += v[r].y; rs.z += v[r].z; rs.w += v[r].w;
+        c += cv[r];
+      }
     }
     float4 e = reinterpret_cast<float4*>(E)[i], s = reinterpret_cast<float4*>(sum_ema)[i];
     s.x = decay * s.x + (1.f - decay) * (rs.x + c * e.x);
@@ -224,9 +242,11 @@ extern "C" int ccvsq_peer_publish(const float* stats, int K, int D, void* const*
   CCVSQ_REQUIRE(((uintptr_t)stats & 15) == 0, CCVSQ_MISALIGNED, "peer_publish: the statistics buffer must be 16-byte aligned");
   PeerPtrs pp = {};
   for (int p = 0; p < world; ++p) pp.p[p] = (uint8_t*)areas[p];
+  // A small grid on purpose: the pushes run NEXT TO the caller's backward pass (side stream) and have its whole duration
+  // to finish; 32 CTAs move W x 1 MB in ~10 us without taking an SM slot on most of the chip from the HBM-bound kernel.
   const size_t n4 = ((size_t)K * D + K) / 4;
   int blocks = (int)((n4 + 255) / 256);
-  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  if (blocks > 32) blocks = 32;
   if (blocks < 1) blocks = 1;
   peer_publish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(stats, pp, K, D, rank, world);
   CCVSQ_LAUNCH_CHECK();
