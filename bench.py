@@ -718,11 +718,20 @@ def main():
                       "quantization of chunk c" % pipe.n_chunks if pipe is not None else "")}
 
     # ---------------- training-mode sub-record (every rank: it contains the design's only collective) ----------------
-    train_rec = None
-    if args.workload == "c2" and not args.no_extras:
-        train_rec = train_record(args, dev, world, cb, z.detach(), barrier)
+    # It runs LAST on rank 0 (after every other measurement of the line, right before printing) and behind a guard: a
+    # failure inside the collective must not cost the line its headline numbers.  The other ranks enter it right away and
+    # wait in its first collective until rank 0 arrives.
+    want_train = args.workload == "c2" and not args.no_extras
+
+    def guarded_train_record():
+        try:
+            return train_record(args, dev, world, cb, z.detach(), barrier)
+        except Exception as e:                                   # noqa: BLE001 — reported in the record
+            return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
     if rank != 0:
+        if want_train:
+            guarded_train_record()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -837,7 +846,7 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "host_issue_ms_per_step": host_issue_ms, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "kernel_breakdown": breakdown, "hbm_kernels": extra, "small_batch": small,
         "ms_per_step_with_kernel_events": ms_total_b / args.steps,
-        "train": train_rec,
+        "train": None,
     }
     if args.workload == "c2" and world == 1 and not args.no_extras:
         # north_star targets that the default workload does not exercise (rank 0, one GPU)
@@ -846,6 +855,8 @@ def main():
         line["encoder_tail"] = encoder_tail_record(dev, peaks())
         if not args.no_cpu_baseline:
             line["index_match"] = index_match_record(dev, args.search_mode)
+    if want_train:
+        line["train"] = guarded_train_record()
     print_result(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
