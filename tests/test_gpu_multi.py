@@ -208,3 +208,37 @@ def test_reference_faithful_ddp_mode_two_ranks():
     assert abs(float(loss) - 0.5 * (l0 + l1)) <= 1e-5 * abs(float(loss))
     torch.testing.assert_close(model.net_q.embedding.weight.grad.cpu(), dE0, rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(model.enc.weight.grad.cpu(), dW0, rtol=1e-3, atol=1e-6)
+
+
+def _empty_shard_worker(rank, world, port, q, exchange):
+    dist = _init(rank, world, port)
+    import vq_oracle
+    from ccvs_b200.quantize import EMAVectorQuantizer
+    dev = torch.device("cuda", rank)
+    z_all, cb = vq_oracle.synth(SHAPE, K, D, "T", seed=79)
+    vq = EMAVectorQuantizer(K, D, 0.25, decay=0.9, sync=True, exchange=exchange).to(dev).train()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb.to(dev))
+        vq.ema_sum.copy_(cb.to(dev))
+        vq.ema_count.fill_(1.0)
+    for step in range(3):
+        # rank 1 has nothing in step 1 (a ragged last batch): it must still join the exchange, with zero statistics
+        z = (z_all if not (rank == 1 and step == 1) else z_all[:0]).to(dev).requires_grad_(True)
+        z_q, loss, _ = vq(z)
+        if z.numel():
+            torch.autograd.backward([z_q, loss], [torch.ones_like(z_q), torch.ones_like(loss)])
+    vq.sync_codebook()
+    torch.cuda.synchronize()
+    q.put((rank, vq.embedding.weight.detach().cpu(), vq.ema_count.cpu()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_an_empty_shard_still_joins_the_exchange(exchange):
+    """A rank whose shard is empty in one step publishes zero statistics: the ranks stay in lock step and end with the
+    same finite codebook (round-1 advisor finding: the exchange used to sum uninitialised memory)."""
+    _need_two_gpus()
+    (_, w0, n0), (_, w1, n1) = _spawn(_empty_shard_worker, 2, exchange)
+    assert torch.equal(w0, w1) and torch.equal(n0, n1)
+    assert bool(torch.isfinite(w0).all()) and bool(torch.isfinite(n0).all())

@@ -219,3 +219,39 @@ def test_deferred_ema_statistics_gloo():
     for _, _, _, resid, cnt in got:
         assert torch.equal(resid, want_resid) and torch.equal(cnt, want_counts)
     assert torch.equal(got[1][1], torch.zeros(6, 4))
+
+
+# ------------------------------------------------------------------------------------------------
+# peer exchange: set-up decisions that need no GPU
+# ------------------------------------------------------------------------------------------------
+def test_peer_exchange_is_off_without_a_process_group_and_validates_the_mode():
+    from ccvs_b200.peer import PeerExchange
+    assert PeerExchange.create(1024, 256, torch.device("cpu")) is None      # no process group: nothing to exchange
+    with pytest.raises(ValueError):
+        EMAVectorQuantizer(64, 16, 0.25, exchange="smoke-signals")
+    vq = EMAVectorQuantizer(64, 16, 0.25, exchange="nccl")
+    assert vq.exchange == "nccl" and vq._peer is None
+    from ccvs_b200 import _lib
+    L = _lib.load()
+    K, D, W = 1024, 256, 8
+    per_slot = (K * D + K + 63) // 64 * 64 * 4
+    assert L.ccvsq_peer_exchange_bytes(K, D, W) == 1024 + 2 * W * per_slot      # header + 2 parities x W inbox slots
+    assert L.ccvsq_peer_exchange_bytes(K, D, 17) == 0 and L.ccvsq_peer_exchange_bytes(0, D, 2) == 0
+
+
+def _peer_gloo_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ccvs_b200.peer import PeerExchange
+    # a CPU device cannot take the peer path: every rank must come back with None WITHOUT entering a collective alone
+    ret[rank] = PeerExchange.create(64, 16, torch.device("cpu")) is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_declines_on_cpu_ranks_gloo():
+    world, port = 2, 29641
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_peer_gloo_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0] and ret[1]
