@@ -134,6 +134,33 @@ def make_inputs_I(workload: str, device, seed: int):
     return z, cb, clips * frames * h * w
 
 
+def stress_record(dev, search_mode: str):
+    """SURVEY 8d asks for BOTH distributions: the step of the default workload on distribution I (fresh-init codebook
+    U(-1/K, 1/K), z ~ N(0,1): 4-5 % of the rows are near ties by construction, so the screen queues / flags far more rows
+    and the FP32 re-scoring and exact fallback carry real work).  Same step as the headline: forward + embed_code."""
+    from ccvs_b200 import VectorQuantizer
+    (clips, frames), D, h, w, K, _ = WORKLOADS["c2"]
+    z, cb, n = make_inputs_I("c2", dev, 1234)
+    vq = VectorQuantizer(K, D, 0.25, search_mode=search_mode).to(dev).eval()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(cb)
+        for _ in range(3):
+            _, _, (_, _, idx) = vq(z)
+            vq.embed_code(idx.view(clips * frames, h, w))
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        a.record()
+        for _ in range(reps):
+            _, _, (_, _, idx) = vq(z)
+            vq.embed_code(idx.view(clips * frames, h, w))
+        b.record()
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    return {"workload": "c2 shape, distribution I (fresh-init codebook, z ~ N(0,1))", "ms_per_step": ms, "value": n / (ms * 1e-3),
+            "unit": UNIT, "note": "stress case: near ties everywhere; the headline distribution is T"}
+
+
 def rows_on_cpu(z):
     """[clips, frames, C, h, w] on the device -> [N, C] rows in the reference's flatten order (quantize.py:40-42)."""
     clips, frames, D, h, w = z.shape
@@ -853,6 +880,7 @@ def main():
         torch.cuda.empty_cache()
         line["roofline_k16384"], line["hbm_kernels_8x8"] = k16384_records(dev, args.search_mode, peaks())
         line["encoder_tail"] = encoder_tail_record(dev, peaks())
+        line["stress_distribution_I"] = stress_record(dev, args.search_mode)
         if not args.no_cpu_baseline:
             line["index_match"] = index_match_record(dev, args.search_mode)
     if want_train:
