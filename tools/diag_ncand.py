@@ -1,3 +1,4 @@
+"""Flag breakdown of the screen queue and forward time by candidate slots (n_cand) on the stress distribution I."""
 import os, sys
 import torch
 sys.path.insert(0, "/root/repo")
