@@ -142,32 +142,6 @@ struct RowLists {
   uint32_t n[2];         // valid entries
 };
 
-// scan the live entries (chunk maximum >= thr) of one ring: count of codes inside the margin, best (score, lowest code)
-__device__ __forceinline__ void scan_ring(uint32_t base, uint32_t hdr, uint32_t n, float thr, uint32_t& within,
-                                          float& best_s, int& best_i) {
-#pragma unroll 1
-  for (uint32_t e = 0; e < n; ++e) {
-    uint32_t code;
-    float mx;
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(code), "=f"(mx) : "r"(hdr + e * ENTRY_BYTES));
-    if (!(mx >= thr)) continue;
-#pragma unroll 2
-    for (int i = 0; i < 8; ++i) {
-      float sc[4];
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3])
-                   : "r"(base + e * ENTRY_BYTES + (uint32_t)i * (BM * 16)));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {      // (padding codes carry -3e38 and never pass)
-        const int c = (int)code + 4 * i + u;
-        within += (sc[u] >= thr) ? 1u : 0u;
-        const bool better = sc[u] > best_s || (sc[u] == best_s && c < best_i);   // lowest code among equal scores
-        best_s = better ? sc[u] : best_s;
-        best_i = better ? c : best_i;
-      }
-    }
-  }
-}
-
 // Fast end-of-sweep scan of one store: how many parked codes are inside the margin, and — valid only when that number
 // is exactly one — which code it is.  Per live chunk: the 8 group maxima (FMNMX3 trees), the number of groups that reach
 // the threshold, and, if that is one, the four scores of that group again (one more shared-memory load).  Two or more
@@ -243,16 +217,54 @@ __device__ __forceinline__ void scan_unique_reg(uint32_t base, uint32_t hdr, uin
 
 // General end-of-sweep path of one row (rows with more than one code inside the margin, dropped chunks, diagnostics):
 // every parked code with score >= runmax - margin, sorted by (score desc, code asc), at most n_cand of them, goes to the
-// re-scoring queue.  Kept out of line (and rolled) so the per-tile loop stays small in the instruction cache.
+// re-scoring queue.  ONE pass over the live entries: every qualifying code is counted, compared with the best, and
+// inserted into a sorted list of CCVSQ_MAX_CAND (score, code) pairs held in registers (an unrolled compare-exchange chain;
+// round 2's first version re-scanned the stores once per candidate slot — five passes at n_cand = 4, which made the
+// screen three times slower on the fresh-init distribution where a third of the rows comes here).
+// Kept out of line so the per-tile loop stays small in the instruction cache.
 template <int NL>
 __device__ __noinline__ void finalize_row(const RowLists L2, float runmax, float margin, bool dropped, int n_cand,
                                           int64_t row, const ScreenOut out) {
   const float thr = runmax - margin;
   uint32_t within = 0;
-  float best_s = -INFINITY;
-  int best_i = -1;
+  float cs[CCVSQ_MAX_CAND];
+  int ci[CCVSQ_MAX_CAND];
 #pragma unroll
-  for (int l = 0; l < NL; ++l) scan_ring(L2.base[l], L2.hdr[l], L2.n[l], thr, within, best_s, best_i);
+  for (int t = 0; t < CCVSQ_MAX_CAND; ++t) { cs[t] = -INFINITY; ci[t] = 0x7fffffff; }
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+#pragma unroll 1
+    for (uint32_t e = 0; e < L2.n[l]; ++e) {
+      uint32_t code;
+      float mx;
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(code), "=f"(mx) : "r"(L2.hdr[l] + e * ENTRY_BYTES));
+      if (!(mx >= thr)) continue;
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        float sc[4];
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3])
+                     : "r"(L2.base[l] + e * ENTRY_BYTES + (uint32_t)i * (BM * 16)));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!(sc[u] >= thr)) continue;           // (padding codes carry -3e38 and never pass)
+          ++within;
+          float vx = sc[u];
+          int vc = (int)code + 4 * i + u;
+#pragma unroll
+          for (int t = 0; t < CCVSQ_MAX_CAND; ++t) {   // insertion: (score desc, code asc)
+            const bool before = (vx > cs[t]) || (vx == cs[t] && vc < ci[t]);
+            const float ts = cs[t];
+            const int tc = ci[t];
+            cs[t] = before ? vx : ts;
+            ci[t] = before ? vc : tc;
+            vx = before ? ts : vx;
+            vc = before ? tc : vc;
+          }
+        }
+      }
+    }
+  }
+  const int best_i = ci[0] == 0x7fffffff ? -1 : ci[0];
   const uint8_t flag = (uint8_t)((within > (uint32_t)n_cand ? 1 : 0) | (dropped ? 2 : 0));
   const bool final_row = within == 1 && flag == 0;
   // (a row of NaN / Inf latents parks nothing: every returned index stays inside [0, K) like torch.argmin's)
@@ -269,45 +281,15 @@ __device__ __noinline__ void finalize_row(const RowLists L2, float runmax, float
     out.dbg_flags[row] = flag;
     out.dbg_margin[row] = margin;
   }
-  float prev_s = INFINITY;
-  int prev_i = -1;
-#pragma unroll 1
-  for (int c = 0; c < n_cand; ++c) {   // repeated selection: next (score desc, code asc) after (prev_s, prev_i)
-    float bs_ = -INFINITY;
-    int bi = 0x7fffffff;
-    if (prev_i != 0x7fffffff) {
 #pragma unroll
-      for (int l = 0; l < NL; ++l) {
-#pragma unroll 1
-        for (uint32_t e = 0; e < L2.n[l]; ++e) {
-          uint32_t code;
-          float mx;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(code), "=f"(mx) : "r"(L2.hdr[l] + e * ENTRY_BYTES));
-          if (!(mx >= thr)) continue;
-#pragma unroll 1
-          for (int i = 0; i < 8; ++i) {
-            float sc[4];
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[0]), "=f"(sc[1]), "=f"(sc[2]), "=f"(sc[3])
-                         : "r"(L2.base[l] + e * ENTRY_BYTES + (uint32_t)i * (BM * 16)));
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int ci = (int)code + 4 * i + u;
-              const float x = sc[u];
-              const bool after_prev = (x < prev_s) || (x == prev_s && ci > prev_i);
-              const bool better = (x > bs_) || (x == bs_ && ci < bi);
-              if (x >= thr && after_prev && better) { bs_ = x; bi = ci; }
-            }
-          }
-        }
+  for (int c = 0; c < CCVSQ_MAX_CAND; ++c) {
+    if (c < n_cand) {
+      const int code_out = ci[c] == 0x7fffffff ? -1 : ci[c];
+      if (slot >= 0) out.q_cand[(int64_t)slot * n_cand + c] = code_out;
+      if (out.dbg_cand) {
+        out.dbg_cand[row * n_cand + c] = code_out;
+        out.dbg_score[row * n_cand + c] = cs[c];
       }
-    }
-    prev_s = bs_;
-    prev_i = bi;
-    const int code_out = bi == 0x7fffffff ? -1 : bi;
-    if (slot >= 0) out.q_cand[(int64_t)slot * n_cand + c] = code_out;
-    if (out.dbg_cand) {
-      out.dbg_cand[row * n_cand + c] = code_out;
-      out.dbg_score[row * n_cand + c] = bs_;
     }
   }
 }
