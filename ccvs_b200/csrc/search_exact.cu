@@ -54,12 +54,24 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
                                              // sees the same count, so the ticket below is skipped consistently)
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  // this CTA's slice of the codebook (whole codebook when gridDim.y == 1), aligned to the slab width
-  const int slice = ((K + (int)gridDim.y - 1) / (int)gridDim.y + XC - 1) / XC * XC;
-  const int k_begin = (int)blockIdx.y * slice;
+  // gridDim.y CTAs share a row tile's codebook sweep ("code slices") or take different row tiles ("row lanes"), decided
+  // HERE from the row count, which only the device knows: few flagged rows (the usual fallback: a few thousand rows on
+  // a fresh-init codebook) -> every CTA of the column takes a slice of the codebook, so that ~100 row tiles still fill the
+  // chip several CTAs deep; many rows (a collapsed codebook flags all of them) -> only as many code slices as the
+  // codebook size asks for (1024 codes each), the other CTAs become row lanes and nothing is staged more often than needed.
+  const int ny = (int)gridDim.y;
+  const int need = min(ny, (K + 1023) / 1024);                    // code slices the codebook size asks for
+  const int64_t tiles = (total_rows + XR - 1) / XR;
+  const bool by_code = !row_list || ny % need != 0 || tiles < 2 * (int64_t)gridDim.x * (ny / need);
+  const int n_code = by_code ? ny : need;                        // code slices in use
+  const int n_lane = ny / n_code;                                // row lanes in use
+  const int code_slice = (int)blockIdx.y % n_code, lane_id = (int)blockIdx.y / n_code;
+  // this CTA's slice of the codebook (whole codebook when there is one slice), aligned to the slab width
+  const int slice = ((K + n_code - 1) / n_code + XC - 1) / XC * XC;
+  const int k_begin = code_slice * slice;
   const int k_end = min(K, k_begin + slice);
 
-  for (int64_t r0 = (int64_t)blockIdx.x * XR; r0 < total_rows; r0 += (int64_t)gridDim.x * XR) {
+  for (int64_t r0 = ((int64_t)blockIdx.x * n_lane + lane_id) * XR; r0 < total_rows; r0 += (int64_t)gridDim.x * n_lane * XR) {
     const int nr = (int)min((int64_t)XR, total_rows - r0);
     __syncthreads();   // previous iteration done with smem
     if (tid < XR) row_id[tid] = (tid < nr) ? (row_list ? row_list[r0 + tid] : r0 + tid) : -1;
@@ -207,9 +219,11 @@ static int launch_exact(const float* z, const Lay& L, const float* E, const floa
   int64_t blocks = (work + XR - 1) / XR;
   int slices = 1;
   if (rows) {
-    // few rows, possibly a large codebook: split K so that a handful of rows still fills the chip
-    slices = (K + 1023) / 1024;
-    if (slices > 16) slices = 16;
+    // few rows, possibly a large codebook: split K so that a handful of rows still fills the chip (the kernel turns
+    // surplus code slices into row lanes when the list is long, see there)
+    const int need = (K + 1023) / 1024 > 16 ? 16 : (K + 1023) / 1024;
+    slices = need;
+    while (slices < 4 && K / (slices + need) >= XC) slices += need;     // a multiple of `need`, at least XC codes per slice
     const int64_t cap = (4 * kNumSMs) / slices;
     if (blocks > cap) blocks = cap;
   } else {
