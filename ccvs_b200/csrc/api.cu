@@ -38,6 +38,10 @@ int enable_smem_impl(const void* kern, size_t bytes) {
   if (slot) { slot->kern = kern; slot->dev = dev; slot->bytes = bytes; }
   return CCVSQ_OK;
 }
+int pdl_off_mask() {
+  static const int m = [] { const char* e = getenv("CCVSQ_NO_PDL_KERNELS"); return e ? atoi(e) : 0; }();
+  return m;
+}
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("CCVSQ_NO_PDL"); return !(e && atoi(e) != 0); }();
   return on;

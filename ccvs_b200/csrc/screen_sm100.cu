@@ -937,7 +937,7 @@ static int launch_screen(const void* E_bf16, const float* z, const Lay& L, const
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = (pdl_enabled() && !(pdl_off_mask() & 1)) ? 2 : 1;
   const int n_tiles = (K + BN - 1) / BN;          // rows [K, n_tiles*BN) of the shadow are padding (bias -3e38)
   CCVSQ_REQUIRE(n_tiles * BN <= K_pad, CCVSQ_BAD_SHAPE, "screen: codebook shadow has %d rows, the sweep needs %d",
                 K_pad, n_tiles * BN);

@@ -47,11 +47,18 @@ __global__ void __launch_bounds__(XT) search_exact_kernel(const float* __restric
   int* red_k = reinterpret_cast<int*>(red_d + XR * 16);   // [XR][16]
   __shared__ int64_t row_id[XR];
 
-  pdl_launch_dependents();
+  // Programmatic dependent launch: the whole-codebook search lets its successor in as early as possible.  The FALLBACK
+  // launch must not — its successor in the forward chain is the assign kernel, whose early CTAs (4 per SM, 32 KiB of
+  // shared memory each, parked in griddepcontrol.wait) would leave this kernel one CTA per SM instead of three exactly
+  // when it has real work (fresh-init codebook: 280 -> 560 us).  So the fallback decides AFTER it has seen the count:
+  // nothing flagged (the usual case) -> release the successor and leave; rows to search -> release it at the end.
+  if (!row_list) pdl_launch_dependents();
   pdl_wait();                                     // the fallback list / the codebook norms come from predecessors
   const int64_t total_rows = row_list ? min((int64_t)row_count[0], max_rows) : L.N;
-  if (row_list && total_rows == 0) return;   // the usual case of the fallback launch: nothing was flagged (every CTA
-                                             // sees the same count, so the ticket below is skipped consistently)
+  if (row_list && total_rows == 0) {         // (every CTA sees the same count, so the ticket below is skipped consistently)
+    pdl_launch_dependents();
+    return;
+  }
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   // gridDim.y CTAs share a row tile's codebook sweep ("code slices") or take different row tiles ("row lanes"), decided
@@ -231,7 +238,7 @@ static int launch_exact(const float* z, const Lay& L, const float* E, const floa
     if (blocks > cap) blocks = cap;
   }
   if (blocks < 1) blocks = 1;
-  CCVSQ_CUDA(launch_pdl(search_exact_kernel, dim3((unsigned)blocks, slices), dim3(XT), smem, st, z, L, E, e_sq, K, rows, keys,
+  CCVSQ_CUDA(launch_pdl_if(!(rows && (pdl_off_mask() & 4)), search_exact_kernel, dim3((unsigned)blocks, slices), dim3(XT), smem, st, z, L, E, e_sq, K, rows, keys,
                         row_count, max_rows, idx));
   CCVSQ_LAUNCH_CHECK();
   return CCVSQ_OK;

@@ -9,6 +9,7 @@
 // inputs (S==1) along the channel index.  The tile row stride is C+1 floats so that both the
 // position-major fill and the channel-major per-row sweeps are bank-conflict free.
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ccvsq {
@@ -145,8 +146,11 @@ __global__ void __launch_bounds__(NT) rescore_queue_kernel(const float* __restri
                                                            int64_t* __restrict__ idx,
                                                            int64_t* __restrict__ fb_rows,
                                                            int32_t* __restrict__ fb_count, int64_t fb_cap) {
-  pdl_launch_dependents();
+  // (launched the ordinary way by default, see ccvsq_rescore: the wait is a no-op then, the release lets the exact fallback —
+  //  which IS a programmatic dependent of this kernel — set itself up while the queue is worked off; under
+  //  CCVSQ_RESCORE_PDL=1 that release comes only after the screen has completed)
   pdl_wait();                               // the queue is written by the screen kernel
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * NW;
   const int total = *q_count;
@@ -685,9 +689,22 @@ extern "C" int ccvsq_rescore(const float* z, ccvsq_layout lay, const float* E, c
   Lay L;
   if (int rc = make_lay(lay, &L)) return rc;
   CCVSQ_REQUIRE(L.D <= 512, CCVSQ_UNSUPPORTED, "rescore: D=%d > 512", L.D);
+  // Grid = what the chip holds at this kernel's occupancy (a grid-stride loop over the queue).
+  // NOT launched as a programmatic dependent of the screen (the rest of the chain is): its CTAs, parked early on the SMs
+  // the screen leaves first, cost the fresh-init regime — a third of the rows queued, thousands in the exact fallback —
+  // a quarter of the whole forward (1 032 -> 763 us at the c2 shape, same-box A/B per kernel: CCVSQ_NO_PDL_KERNELS),
+  // while the trained-codebook regime gains only the ~1 us of launch latency the early start hides (230.7 -> 231.8 us).
+  // CCVSQ_RESCORE_PDL=1 restores the early launch for A/B runs.
+  static const bool rescore_pdl = [] { const char* e = getenv("CCVSQ_RESCORE_PDL"); return e && atoi(e) != 0; }();
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int n = 0;
+    CCVSQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rescore_queue_kernel, NT, 0));
+    per_sm = n > 0 ? n : 4;
+  }
   int64_t blocks = (L.N + NW - 1) / NW;
-  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-  CCVSQ_CUDA(launch_pdl(rescore_queue_kernel, dim3((unsigned)blocks), dim3(NT), 0, (cudaStream_t)stream, z, L, E, e_sq, K,
+  if (blocks > (int64_t)kNumSMs * per_sm) blocks = (int64_t)kNumSMs * per_sm;
+  CCVSQ_CUDA(launch_pdl_if(rescore_pdl && !(pdl_off_mask() & 2), rescore_queue_kernel, dim3((unsigned)blocks), dim3(NT), 0, (cudaStream_t)stream, z, L, E, e_sq, K,
                         n_cand, queue_count, queue_rows, queue_cand, queue_flags, idx, fallback_ws, fallback_count,
                         fallback_capacity));
   return CCVSQ_OK;

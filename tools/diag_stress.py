@@ -23,3 +23,15 @@ for dist in ("T", "I"):
     s = ops.PROFILER.summary()
     ops.PROFILER.reset(timing=False)
     print(f"{wl} dist {dist}: queued {int(q.count)} of {n}  " + "  ".join(f"{k[6:]} {t / c * 1e3:.1f} us" for k, (c, t) in s.items()))
+    # the rest of the step on the same indices: assign (z_q, loss, counts) and the decode gather
+    ops.PROFILER.reset(timing=True)
+    for it in range(4):
+        if it == 1:
+            torch.cuda.synchronize(); ops.PROFILER.reset(timing=True)
+        ops.assign(z, lay, cb, idx)
+        ops.gather(idx, cb)
+    torch.cuda.synchronize()
+    s = ops.PROFILER.summary()
+    ops.PROFILER.reset(timing=False)
+    used = int(torch.bincount(idx, minlength=K).ne(0).sum())
+    print(f"   assign / gather on these indices: " + "  ".join(f"{k[6:]} {t / c * 1e3:.1f} us" for k, (c, t) in s.items()) + f"   codes in use {used} of {K}, max share {float(torch.bincount(idx, minlength=K).max()) / n:.4f}")
