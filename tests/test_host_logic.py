@@ -250,7 +250,7 @@ def _peer_gloo_worker(rank, world, port, ret):
 
 
 def test_peer_exchange_declines_on_cpu_ranks_gloo():
-    world, port = 2, 29641
+    world, port = 2, 33500 + os.getpid() % 2000
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_peer_gloo_worker, args=(world, port, ret), nprocs=world, join=True)
