@@ -308,6 +308,12 @@ __device__ __forceinline__ void load_chunk(float (&v)[32], const float* __restri
       const float4 t = __ldg(p4 + i);
       v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
     }
+  } else if (S == 256) {        // the BASELINE layouts (16x16 and 8x8 latent frames): the 32 offsets become immediates
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __ldg(p + i * 256);
+  } else if (S == 64) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __ldg(p + i * 64);
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __ldg(p + (int64_t)i * S);
